@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Bloom-filter radix join (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c0|c3|...]
+
+A "step" is one complete join (Bloom build over R, S pre-filter, radix partitioning, per-partition build+probe)
+over one batch of synthetic input with the reference generator's key multiset. `value` is timed with CUDA
+events on the library's own stream with the inputs resident in HBM (the reference's timed region: relations
+in memory, filter allocated and zeroed beforehand); `e2e` goes through the reference-facing C-ABI call
+BPRO()/PRO() with pinned HOST buffers, host->device copies and the result read-back inside the timed region.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libref.so, compiled from /root/reference/src in
+the authoring container) on the box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (r, s, q, bloom variant or None, m, k, B, description)
+    "c1": (128_000_000, 1_024_000_000, 0.01, 0, 1 << 30, 1, 512,
+           "README canonical: -r 128000000 -s 1024000000 -q 0.01 -b basic -m 1073741824 -k 1"),
+    "c0": (16_000_000, 256_000_000, 0.01, 0, 1 << 27, 1, 512,
+           "PR1 ref: -r 16000000 -s 256000000 -q 0.01 -m 134217728 -k 1"),
+    "c1_blocked": (128_000_000, 1_024_000_000, 0.01, 1, 1 << 30, 4, 256,
+                   "canonical inputs, -b blocked -B 256 -k 4"),
+    "c3": (128_000_000, 128_000_000, 1.0, None, 0, 0, 0, "Workload B plain PRO: -r 128000000 -s 128000000"),
+    "small": (1_000_000, 8_000_000, 0.01, 0, 1 << 23, 1, 512, "1M x 8M smoke-sized"),
+}
+METRIC = "M input tuples/s ((|R|+|S|)/time)"
+UNIT = "Mtuples/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if c > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_reference_sample(wl, scale: int, nthreads: int, H, reps: int = 1):
+    """The unmodified reference on the host cores, on a 1/scale copy of the workload (same |S|/|R|, q, m/|R|, k)."""
+    import oracle
+    r, s, q, variant, m, k, B, _ = wl
+    r2, s2, m2 = r // scale, s // scale, max(m // scale, 8) if variant is not None else 0
+    dR = H.DeviceRelation.generate(0, r2, r2, 1.0, 1)
+    dS = H.DeviceRelation.generate(1, s2, r2, q, 2)
+    R, S = dR.download(), dS.download()
+    dR.free()
+    dS.free()
+    use_ref = oracle.ref_available()
+    times, res = [], None
+    for _ in range(reps):
+        if use_ref:
+            res = oracle.ref_join(R, S, "PRO", nthreads, variant is not None, variant or 0, m2 or 8, k, B or 512)
+            times.append(res["total_usecs"] * 1e-6)
+        else:
+            t0 = time.perf_counter()
+            res = oracle.join(R, S, variant is not None, variant or 0, m2 or 8, k, B or 512)
+            times.append(time.perf_counter() - t0)
+    sample = (f"1/{scale} of the workload: r={r2} s={s2} q={q} "
+              + (f"{'basic' if variant == 0 else 'blocked'} m={m2} k={k} B={B}" if variant is not None else "no filter")
+              + ("; reference BPRO/PRO TOTAL-TIME-USECS" if use_ref else "; oracle port wall clock"))
+    return {"times": times, "tuples": r2 + s2, "kind": "reference" if use_ref else "port",
+            "cores": nthreads if use_ref else 1, "sample": sample, "result": res}
+
+
+def run_reference_arm(args, wl_name, wl):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    import hwbloomradixjoin_b200 as H
+    from hwbloomradixjoin_b200 import build
+    build.build_library()
+    H.set_quiet(True)
+    nthreads = os.cpu_count() or 1
+    scale = args.ref_scale
+    total = args.steps + args.warmup
+    out = cpu_reference_sample(wl, scale, nthreads, H, reps=total)
+    times = out["times"][args.warmup:]
+    secs = sum(times)
+    value = out["tuples"] * len(times) / secs / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / len(times) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": wl[7], "name": wl_name, "sample": out["sample"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": out["cores"], "kind": out["kind"],
+                             "sample": out["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-scale", type=int, default=4, help="the CPU arm runs on 1/ref-scale of the workload")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps,5))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, args.workload, wl)
+
+    rank, world, local = dist_env()
+    if world > 1 or args.gpus > 1:
+        from hwbloomradixjoin_b200 import bench_dist
+        return bench_dist.main(args, wl, METRIC, UNIT, measured_peak, ClockSampler)
+
+    import hwbloomradixjoin_b200 as H
+    from hwbloomradixjoin_b200 import build
+    build.build_library()
+    if H.device_count() < 1:
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
+        return 1
+    H.set_quiet(True)
+    r, s, q, variant, m, k, B, desc = wl
+    bloom = H.BloomFilterArgs(variant, m, k, B) if variant is not None else None
+
+    # ---- inputs (reference generator's multiset, generated on the device; synthetic) ----
+    dR = H.DeviceRelation.generate(0, r, r, 1.0, 1)
+    dS = H.DeviceRelation.generate(1, s, r, q, 2)
+
+    # ---- device-resident leg: `value` ----
+    for _ in range(max(args.warmup, 3)):
+        res = H.join_device(dR, dS, bloom)
+    sampler = ClockSampler(local)
+    sampler.start()
+    per_step, stats = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = H.join_device(dR, dS, bloom)
+        per_step.append(res.stats["ms_total"])
+        stats.append(res.stats)
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms_total = sum(per_step)
+    ms_per_step = ms_total / args.steps
+    value = (r + s) / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (S-side probe + compaction) ----
+    peak, peak_src = measured_peak()
+    F = res.filtered if bloom is not None else s
+    phases = {p: statistics.mean(st[p] for st in stats) for p in
+              ("ms_build", "ms_part_r", "ms_probe", "ms_part_s", "ms_join", "ms_memset")}
+    if bloom is not None:
+        dom_name = "k_probe_compact (K2: S probe + compaction + survivor histogram)"
+        dom_bytes = 8 * s + 8 * F + m // 8          # S read once, survivors written once, filter read once
+        dom_ms = phases["ms_probe"]
+    else:
+        dom_name = "k_scatter (K4: radix scatter of S)"
+        dom_bytes = 16 * s
+        dom_ms = phases["ms_part_s"]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    b_alg = (24 * r + 8 * s + 16 * F + 2 * (m // 8)) if bloom is not None else (24 * r + 24 * s)
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch_set": dom_bytes, "ms_per_launch_set": dom_ms,
+                "launches_per_step": stats[-1]["range_passes"] if bloom is not None else 1,
+                "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,
+                               "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # ---- host-buffer leg through the C ABI: `e2e` ----
+    from hwbloomradixjoin_b200 import _native as N
+    L = N.load()
+    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    hR = L.hwbrj_host_alloc(r * 8)
+    hS = L.hwbrj_host_alloc(s * 8)
+    L.hwbrj_rel_download(dR._h, hR)
+    L.hwbrj_rel_download(dS._h, hS)
+    relR = N.RelationT(hR, r)
+    relS = N.RelationT(hS, s)
+    cargs = bloom.to_c() if bloom is not None else None
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+
+    def host_call():
+        if bloom is not None:
+            p = L.BPRO(C.byref(relR), C.byref(relS), 1, C.byref(cargs))
+        else:
+            p = L.PRO(C.byref(relR), C.byref(relS), 1)
+        tot = p.contents.totalresults
+        libc.free(C.cast(p, C.c_void_p))
+        return tot
+    host_call()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tot = host_call()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert tot == res.totalresults
+    st = N.StatsT()
+    L.hwbrj_last_stats(C.byref(st))
+    e2e = {"value": (r + s) / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(st.h2d_bytes),
+           "d2h_bytes_per_step": int(st.d2h_bytes), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "ms_h2d": st.ms_h2d, "api": "BPRO(relation_t*,relation_t*,int,bloom_filter_args_t*)" if bloom else "PRO(...)"}
+    L.hwbrj_host_free(hR)
+    L.hwbrj_host_free(hS)
+    dR.free()
+    dS.free()
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        nthreads = os.cpu_count() or 1
+        out = cpu_reference_sample(wl, args.ref_scale, nthreads, H, reps=1)
+        cpu = {"value": out["tuples"] / out["times"][0] / 1e6, "unit": UNIT, "cores": out["cores"], "kind": out["kind"],
+               "sample": out["sample"], "seconds": out["times"][0]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q,
+                       "bloom": None if bloom is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
+                       "radix_bits": stats[-1]["radix_bits"], "range_passes": stats[-1]["range_passes"],
+                       "l2": f"inputs are {((r + s) * 8) >> 20} MiB per step, larger than the 126 MB L2; no flush needed",
+                       "timed_region": "CUDA events on the library stream; filter/scratch zero-fill excluded as in the reference (reported as ms_memset)"},
+            "results": {"matches": res.totalresults, "filtered": res.filtered, "checksum_pair": res.checksum_pair},
+            "phases_ms": phases, "wall_ms_per_step": wall / args.steps * 1e3,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(sum(st_["kernel_launches"] for st_ in stats)), "clocks": clocks}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

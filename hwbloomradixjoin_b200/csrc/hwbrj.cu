@@ -1,0 +1,631 @@
+// hwbrj.cu -- host side of libhwbrj_cuda.so: workspace, the single-GPU join pipeline and the C ABI of
+// include/hwbrj.h. Mirrors the reference's join_init_run()/prj_thread() orchestration
+// (parallel_radix_join_bloom.c:1060-1506,1561-1778) as one CUDA stream of kernels with no host round trip
+// between phases; the pthread barriers of the reference become kernel boundaries.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/hwbrj.h"
+#include "kernels.cuh"
+#include "dist.cuh"
+
+namespace hwbrj {
+
+[[noreturn]] void die(const char* fmt, ...) {
+    // the reference's error style: print and exit (parallel_radix_join_bloom.c:64-71, bloom_filter.c:16-23)
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stdout, "[ERROR] hwbrj: ");
+    vfprintf(stdout, fmt, ap);
+    fprintf(stdout, "\n");
+    fflush(stdout);
+    va_end(ap);
+    exit(EXIT_FAILURE);
+}
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) die("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        size_t want = bytes + (bytes >> 4) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) die("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        cap = want;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// small control block living in one allocation (zeroed with one memset per join)
+struct Control {
+    unsigned long long survivors;  // K2 output cursor == filtered
+    unsigned long long n_s_static; // unused slot (keeps 16B alignment)
+    JoinAccum acc;
+    uint32_t item_counter;
+    uint32_t pad[3];
+};
+
+struct Ctx {
+    bool inited = false;
+    int dev = 0;
+    int sms = 0;
+    int clock_khz = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    uint32_t* d_crc = nullptr;
+    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, ctrl, rt1, rp, sc, st1, inR, inS, scratch;
+    hwbrj_stats_t last;
+    bool quiet = false;
+    int radix_bits_override = 0;
+    int range_passes_override = 0;
+    std::mutex mu;
+};
+
+static Ctx g;
+
+static void init_ctx() {
+    if (g.inited) return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        die("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    CK(cudaGetDevice(&g.dev));
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, g.dev));
+    g.sms = pr.multiProcessorCount;
+    g.clock_khz = pr.clockRate;
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
+    CrcTables T;
+    crc_tables_fill(T);
+    CK(cudaMalloc(&g.d_crc, sizeof(T)));
+    CK(cudaMemcpy(g.d_crc, &T, sizeof(T), cudaMemcpyHostToDevice));
+    const int hist_smem = ((1 << kMaxRadixBits) + 1024) * 4;
+    CK(cudaFuncSetAttribute(k_build_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    CK(cudaFuncSetAttribute(k_probe_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            hist_smem + kProbeTile * 8));
+    CK(cudaFuncSetAttribute(k_join, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
+    if (const char* s = getenv("HWBRJ_RADIX_BITS")) g.radix_bits_override = atoi(s);
+    if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
+    if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
+    memset(&g.last, 0, sizeof(g.last));
+    g.inited = true;
+}
+
+static int ilog2_u64(uint64_t v) {
+    int l = 0;
+    while ((1ull << (l + 1)) <= v) l++;
+    return l;
+}
+
+static int check_args_impl(const bloom_filter_args_t* a, bool print) {
+    // bloom_filter.c:26-34
+    if (a->m == 0 || (a->m & (a->m - 1)) != 0) {
+        if (print) printf("m must be a power of 2");
+        return 1;
+    }
+    if (a->m > (1ull << 32)) {  // mod_m()/size are uint32_t in the reference (bloom_filter.c:60-63,75)
+        if (print) printf("m must be at most 2^32");
+        return 4;
+    }
+    if (a->variant != BASIC) {
+        if (a->B == 0 || (a->B & (a->B - 1)) != 0) {
+            if (print) printf("B must be a power 2");
+            return 2;
+        }
+        if (a->B < 8 || a->m % a->B != 0) {  // B/8 bytes per block (bloom_filter.c:129)
+            if (print) printf("m must be a multiple of B");
+            return 3;
+        }
+    }
+    return 0;
+}
+
+static BloomParams make_bloom(const bloom_filter_args_t* a, uint32_t seed, uint32_t* filter) {
+    BloomParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.filter = filter;
+    bp.k = (uint32_t)a->k;
+    bp.seed = seed;
+    bp.blocked = a->variant == BLOCKED ? 1u : 0u;
+    if (bp.blocked) {
+        bp.size_mask = (uint32_t)(a->B - 1);
+        bp.nblocks_mask = (uint32_t)(a->m / a->B - 1);
+        bp.log2B = (uint32_t)ilog2_u64(a->B);
+    } else {
+        bp.size_mask = (uint32_t)(a->m - 1);  // m == 2^32 -> 0xFFFFFFFF
+    }
+    bp.nranges = 1;
+    bp.range_shift = 0;
+    bp.range_id = 0;
+    return bp;
+}
+
+// number of filter range passes: keep the actively probed part of the filter L2-resident (<= 64 MiB).
+// Only valid when all k bits of a key fall into one range: k <= 1 or BLOCKED.
+static int pick_ranges(const bloom_filter_args_t* a) {
+    if (a->variant == BASIC && a->k > 1) return 1;
+    uint64_t bytes = a->m / 8;
+    int nr = 1;
+    if (g.range_passes_override > 0) nr = g.range_passes_override;
+    else
+        while ((bytes / nr) > (64ull << 20)) nr <<= 1;
+    // must be a power of two and leave ranges >= one block / one word
+    while (nr & (nr - 1)) nr &= nr - 1;
+    uint64_t min_range_bits = a->variant == BLOCKED ? std::max<uint64_t>(a->B, 32) : 32;
+    while (nr > 1 && a->m / nr < min_range_bits) nr >>= 1;
+    return std::max(nr, 1);
+}
+
+static int pick_bits(uint64_t nR) {
+    if (g.radix_bits_override > 0) return std::min(g.radix_bits_override, (int)kMaxRadixBits);
+    int b = 0;
+    while (b < kMaxRadixBits && (nR >> b) > (uint64_t)(kTableCap * 3 / 4)) b++;
+    return b;
+}
+
+struct Partitioned {
+    const uint2* data;
+    const uint32_t* off;
+};
+
+// histogram already in `hist`; runs scan + 1 or 2 scatter passes. n_dev (optional) = device-side tuple count.
+static const uint2* run_partition(const uint2* in, uint64_t n, const unsigned long long* n_dev, int bits, int b2,
+                                  uint32_t* hist, uint32_t* off, uint2* t1, uint2* t2, int& launches) {
+    const uint32_t P = 1u << bits;
+    const uint32_t pmask = P - 1u;
+    const int b1 = bits - b2;
+    k_scan<<<1, 1024, 0, g.stream>>>(hist, P, (uint32_t)b2, off, g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(),
+                                     g.tiles.as<uint32_t>());
+    launches++;
+    const int grid = g.sms * 4;
+    k_scatter<1><<<grid, kScatterThreads, 0, g.stream>>>(in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off,
+                                                        g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pmask,
+                                                        (uint32_t)b2, 1u << b1);
+    launches++;
+    if (b2 == 0) return t1;
+    k_scatter<2><<<grid, kScatterThreads, 0, g.stream>>>(t1, t2, nullptr, n, off, g.tiles.as<uint32_t>(),
+                                                        g.cur2.as<uint32_t>(), pmask, (uint32_t)b2, 1u << b2);
+    launches++;
+    return t2;
+}
+
+static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t* args) {
+    const size_t P = 1u << kMaxRadixBits;
+    if (args) g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
+    g.histR.ensure(P * 4);
+    g.histS.ensure(P * 4);
+    g.offR.ensure((P + 1) * 4);
+    g.offS.ensure((P + 1) * 4);
+    g.cur1.ensure(((size_t)1 << kMaxLevelBits) * 4);
+    g.cur2.ensure(P * 4);
+    g.tiles.ensure((((size_t)1 << kMaxLevelBits) + 1) * 4);
+    g.work.ensure((P + 1) * 4);
+    g.ctrl.ensure(sizeof(Control));
+    g.rt1.ensure(std::max<uint64_t>(nR, 1) * 8);
+    g.rp.ensure(std::max<uint64_t>(nR, 1) * 8);
+    g.sc.ensure(std::max<uint64_t>(nS, 1) * 8);
+    g.st1.ensure(std::max<uint64_t>(nS, 1) * 8);
+}
+
+// The join on device-resident relations. args == nullptr: plain radix join.
+static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS, const bloom_filter_args_t* args,
+                     hwbrj_stats_t& st) {
+    if (nR >= (1ull << 32) || nS >= (1ull << 32)) die("relations of 2^32 or more tuples are not supported");
+    if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
+    ensure_workspace(nR, nS, args);
+    const int bits = pick_bits(nR);
+    const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
+    const uint32_t P = 1u << bits;
+    const uint32_t pmask = P - 1u;
+    int launches = 0;
+    Control* ctrl = g.ctrl.as<Control>();
+
+    // ---- untimed set-up (the reference allocates and zeroes its filter before the timed region, :1583) ----
+    CK(cudaEventRecord(g.ev[0], g.stream));
+    if (args) CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
+    CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
+    CK(cudaMemsetAsync(g.histS.p, 0, P * 4, g.stream));
+    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
+
+    // ---- timed region ----------------------------------------------------------------------------------------
+    CK(cudaEventRecord(g.ev[1], g.stream));
+    BloomParams bp;
+    memset(&bp, 0, sizeof(bp));
+    int nranges = 1;
+    const int hist_smem = (int)((P + 1024) * 4);
+    const int grid_hist = g.sms * 2;
+    if (args) {
+        bp = make_bloom(args, 42u, g.filter.as<uint32_t>());  // seed 42: parallel_radix_join_bloom.c:1583,1823
+        nranges = pick_ranges(args);
+        bp.nranges = (uint32_t)nranges;
+        bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+        for (int r = 0; r < nranges; r++) {
+            bp.range_id = (uint32_t)r;
+            k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+            launches++;
+        }
+    } else {
+        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+        launches++;
+    }
+    CK(cudaEventRecord(g.ev[2], g.stream));
+    const uint2* Rp = run_partition(dR, nR, nullptr, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(),
+                                    g.rt1.as<uint2>(), g.rp.as<uint2>(), launches);
+    CK(cudaEventRecord(g.ev[3], g.stream));
+    const uint2* Sin = dS;
+    const unsigned long long* n_dev = nullptr;
+    if (args) {
+        const int probe_smem = hist_smem + kProbeTile * 8;
+        for (int r = 0; r < nranges; r++) {
+            bp.range_id = (uint32_t)r;
+            k_probe_compact<<<g.sms * 2, kProbeThreads, probe_smem, g.stream>>>(
+                dS, nS, bp, g.d_crc, g.sc.as<uint2>(), &ctrl->survivors, g.histS.as<uint32_t>(), pmask);
+            launches++;
+        }
+        Sin = g.sc.as<uint2>();
+        n_dev = &ctrl->survivors;
+    } else {
+        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dS, nS, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
+        launches++;
+    }
+    CK(cudaEventRecord(g.ev[4], g.stream));
+    // with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc
+    const uint2* Sp = run_partition(Sin, nS, n_dev, bits, b2, g.histS.as<uint32_t>(), g.offS.as<uint32_t>(),
+                                    g.st1.as<uint2>(), g.sc.as<uint2>(), launches);
+    CK(cudaEventRecord(g.ev[5], g.stream));
+    k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>());
+    launches++;
+    k_join<<<g.sms * 2, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
+        Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
+        &ctrl->item_counter, &ctrl->acc);
+    launches++;
+    CK(cudaEventRecord(g.ev[6], g.stream));
+    Control h;
+    CK(cudaMemcpyAsync(&h, ctrl, sizeof(Control), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+
+    auto ms = [&](int a, int b) {
+        float v = 0;
+        CK(cudaEventElapsedTime(&v, g.ev[a], g.ev[b]));
+        return v;
+    };
+    st.matches = (int64_t)h.acc.matches;
+    st.filtered = args ? (int64_t)h.survivors : -1;
+    st.checksum_pair = h.acc.cpair;
+    st.checksum_rpay = h.acc.crpay;
+    st.checksum_spay = h.acc.cspay;
+    st.checksum_key = h.acc.ckey;
+    st.ms_memset = ms(0, 1);
+    st.ms_total = ms(1, 6);
+    st.ms_build = ms(1, 2);
+    st.ms_part_r = ms(2, 3);
+    st.ms_probe = ms(3, 4);
+    st.ms_part_s = ms(4, 5);
+    st.ms_join = ms(5, 6);
+    st.kernel_launches = launches;
+    st.radix_bits = bits;
+    st.range_passes = nranges;
+    st.n_gpus = 1;
+    st.d2h_bytes += sizeof(Control);
+}
+
+static void print_reference_lines(const hwbrj_stats_t& st, uint64_t nS, bool bloom_line) {
+    if (g.quiet) return;
+    // stdout contract of parallel_radix_join_bloom.c:1253 and print_timing (:1510-1547)
+    if (bloom_line) fprintf(stdout, "S-tuples after filter: %d\n", (int)st.filtered);
+    const double total_us = st.ms_total * 1000.0;
+    const double part_us = (st.ms_build + st.ms_part_r + st.ms_probe + st.ms_part_s) * 1000.0;
+    const double join_us = st.ms_join * 1000.0;
+    const double mhz = g.clock_khz / 1000.0;
+    unsigned long long cyc_total = (unsigned long long)(total_us * mhz);
+    unsigned long long cyc_part = (unsigned long long)(part_us * mhz);
+    unsigned long long cyc_build = (unsigned long long)(st.ms_build * 1000.0 * mhz);
+    fprintf(stdout, "RUNTIME TOTAL, BUILD, PART (cycles): \n");
+    fprintf(stdout, "%llu \t %llu \t %llu ", cyc_total, cyc_build, cyc_part);
+    fprintf(stdout, "\n");
+    fprintf(stdout, "TOTAL-TIME-USECS, TOTAL-TUPLES, NSEC-PER-TUPLE: \n");
+    fprintf(stdout, "%.4lf \t %llu \t ", total_us, (unsigned long long)st.matches);
+    fprintf(stdout, "%.4lf ", nS ? total_us * 1000.0 / (double)nS : 0.0);
+    fprintf(stdout, "\n");
+    fprintf(stdout, "PARTITION-TIME-USECS, PROBE-TIME-USECS, JOIN-TIME-USECS: \n");
+    fprintf(stdout, "%.4lf \t %.4lf\t %.4lf \n", part_us, join_us, join_us);
+    fprintf(stdout, "H2D-COPY-USECS, END-TO-END-USECS, GPUS: \n");
+    fprintf(stdout, "%.4lf \t %.4lf\t %d \n", st.ms_h2d * 1000.0, st.ms_e2e * 1000.0, st.n_gpus);
+    fflush(stdout);
+}
+
+static void h2d(void* dst, const void* src, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+}
+
+// host-buffer entry: copy in, join, fill result_t (join_init_run, :1561-1778)
+static result_t* host_join(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args,
+                           bool print_filtered) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!relR || !relS) die("NULL relation");
+    auto t0 = std::chrono::steady_clock::now();
+    hwbrj_stats_t st;
+    memset(&st, 0, sizeof(st));
+    const uint64_t nR = relR->num_tuples, nS = relS->num_tuples;
+    g.inR.ensure(std::max<uint64_t>(nR, 2) * 8);
+    g.inS.ensure(std::max<uint64_t>(nS, 2) * 8);
+    CK(cudaEventRecord(g.ev[7], g.stream));
+    h2d(g.inR.p, relR->tuples, nR * 8);
+    h2d(g.inS.p, relS->tuples, nS * 8);
+    CK(cudaEventRecord(g.ev[0], g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[7], g.ev[0]));
+    st.h2d_bytes = (nR + nS) * 8;
+    run_join(g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, st);
+    st.ms_e2e = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    g.last = st;
+    print_reference_lines(st, nS, args != nullptr && print_filtered);
+    result_t* res = (result_t*)malloc(sizeof(result_t));
+    if (!res) die("malloc(result_t) failed");
+    res->totalresults = st.matches;
+    res->resultlist = nullptr;  // only allocated under JOIN_RESULT_MATERIALIZE in the reference (:1598-1601)
+    res->nthreads = nthreads;
+    return res;
+}
+
+}  // namespace hwbrj
+
+using namespace hwbrj;
+
+extern "C" {
+
+// ---- Part 1: the reference's entry points ---------------------------------------------------------------------
+result_t* BPRO(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args) {
+    if (!args) die("BPRO: NULL bloom_filter_args");
+    return host_join(relR, relS, nthreads, args, true);
+}
+result_t* BPRH(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args) {
+    return BPRO(relR, relS, nthreads, args);
+}
+result_t* BPRHO(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args) {
+    return BPRO(relR, relS, nthreads, args);
+}
+result_t* BRJ(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args) {
+    if (!args) die("BRJ: NULL bloom_filter_args");
+    result_t* r = host_join(relR, relS, nthreads, args, false);  // BRJ does not print the filtered count
+    r->nthreads = 1;                                             // :1974
+    return r;
+}
+result_t* PRO(relation_t* relR, relation_t* relS, int nthreads) { return host_join(relR, relS, nthreads, nullptr, false); }
+result_t* PRH(relation_t* relR, relation_t* relS, int nthreads) { return PRO(relR, relS, nthreads); }
+result_t* PRHO(relation_t* relR, relation_t* relS, int nthreads) { return PRO(relR, relS, nthreads); }
+result_t* RJ(relation_t* relR, relation_t* relS, int nthreads) {
+    result_t* r = host_join(relR, relS, nthreads, nullptr, false);
+    r->nthreads = 1;
+    return r;
+}
+
+// ---- Part 2: extensions ---------------------------------------------------------------------------------------
+int hwbrj_last_stats(hwbrj_stats_t* out) {
+    if (!out) return -1;
+    *out = g.last;
+    return 0;
+}
+int64_t hwbrj_last_filtered(void) { return g.last.filtered; }
+uint64_t hwbrj_last_checksum(void) { return g.last.checksum_pair; }
+void hwbrj_set_quiet(int quiet) { g.quiet = quiet != 0; }
+void hwbrj_set_radix_bits(int bits) { g.radix_bits_override = bits; }
+void hwbrj_set_range_passes(int passes) { g.range_passes_override = passes; }
+const char* hwbrj_version(void) { return "hwbrj-b200 0.1 (sm_100a)"; }
+int hwbrj_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int hwbrj_check_args(const bloom_filter_args_t* args) { return args ? check_args_impl(args, true) : 1; }
+
+struct hwbrj_rel {
+    uint2* d;
+    uint64_t n;
+};
+
+hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    hwbrj_rel_t* r = new hwbrj_rel;
+    r->n = n;
+    CK(cudaMalloc(&r->d, std::max<uint64_t>(n, 2) * 8));
+    if (n) CK(cudaMemcpy(r->d, tuples, n * 8, cudaMemcpyHostToDevice));
+    return r;
+}
+
+hwbrj_rel_t* hwbrj_rel_generate(int kind, uint64_t n, uint64_t r, double q, uint64_t seed) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    hwbrj_rel_t* rel = new hwbrj_rel;
+    rel->n = n;
+    CK(cudaMalloc(&rel->d, std::max<uint64_t>(n, 2) * 8));
+    if (n) {
+        // generator.c:344: ntuples_above = num_tuples * (1 - selectivity)
+        uint64_t na = kind == 1 ? (uint64_t)((double)n * (1.0 - q)) : 0;
+        uint64_t nb = n - na;
+        int bitsn = 1;
+        while ((1ull << bitsn) < n) bitsn++;
+        uint32_t half = (uint32_t)((bitsn + 1) / 2);
+        k_generate<<<g.sms * 8, 256, 0, g.stream>>>(rel->d, n, kind, r ? r : 1, nb, half, seed * 0x9e3779b97f4a7c15ULL + 12345);
+        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaGetLastError());
+    }
+    return rel;
+}
+
+int hwbrj_rel_download(const hwbrj_rel_t* rel, tuple_t* out) {
+    if (!rel || !out) return -1;
+    if (rel->n) CK(cudaMemcpy(out, rel->d, rel->n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+uint64_t hwbrj_rel_size(const hwbrj_rel_t* rel) { return rel ? rel->n : 0; }
+void hwbrj_rel_free(hwbrj_rel_t* rel) {
+    if (!rel) return;
+    cudaFree(rel->d);
+    delete rel;
+}
+
+int hwbrj_join_device(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, hwbrj_stats_t* out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!R || !S) return -1;
+    hwbrj_stats_t st;
+    memset(&st, 0, sizeof(st));
+    run_join(R->d, R->n, S->d, S->n, args, st);
+    g.last = st;
+    if (out) *out = st;
+    return 0;
+}
+
+void* hwbrj_host_alloc(uint64_t bytes) {
+    init_ctx();
+    void* p = nullptr;
+    CK(cudaHostAlloc(&p, std::max<uint64_t>(bytes, 8), cudaHostAllocDefault));
+    return p;
+}
+void hwbrj_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int hwbrj_hash_many(int which, uint32_t seed, const int32_t* keys, uint64_t n, uint32_t* out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (which < 0 || which > 9) return -1;
+    if (!n) return 0;
+    g.scratch.ensure(n * 8);
+    int32_t* dk = g.scratch.as<int32_t>();
+    uint32_t* dout = reinterpret_cast<uint32_t*>(dk + n);
+    CK(cudaMemcpyAsync(dk, keys, n * 4, cudaMemcpyHostToDevice, g.stream));
+    k_hash_many<<<g.sms * 4, 256, 0, g.stream>>>(which, seed, dk, n, dout);
+    CK(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hwbrj_bloom_build(const tuple_t* R, uint64_t nR, const bloom_filter_args_t* args, uint32_t seed,
+                      unsigned char* bitmap_out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!args || check_args_impl(args, true)) return -1;
+    g.inR.ensure(std::max<uint64_t>(nR, 2) * 8);
+    g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
+    g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
+    h2d(g.inR.p, R, nR * 8);
+    CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
+    CK(cudaMemsetAsync(g.histR.p, 0, 4, g.stream));
+    BloomParams bp = make_bloom(args, seed, g.filter.as<uint32_t>());
+    int nranges = pick_ranges(args);
+    bp.nranges = (uint32_t)nranges;
+    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + 1024) * 4, g.stream>>>(g.inR.as<uint2>(), nR, bp, g.d_crc,
+                                                                          g.histR.as<uint32_t>(), 0u);
+    }
+    CK(cudaMemcpyAsync(bitmap_out, g.filter.p, args->m / 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_t nS, const bloom_filter_args_t* args,
+                          uint32_t seed, tuple_t* survivors_out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!args || check_args_impl(args, true)) return -1;
+    g.inS.ensure(std::max<uint64_t>(nS, 2) * 8);
+    g.sc.ensure(std::max<uint64_t>(nS, 1) * 8);
+    g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
+    g.histS.ensure(((size_t)1 << kMaxRadixBits) * 4);
+    g.ctrl.ensure(sizeof(Control));
+    h2d(g.inS.p, S, nS * 8);
+    h2d(g.filter.p, bitmap, args->m / 8);
+    CK(cudaMemsetAsync(g.histS.p, 0, 4, g.stream));
+    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
+    Control* ctrl = g.ctrl.as<Control>();
+    BloomParams bp = make_bloom(args, seed, g.filter.as<uint32_t>());
+    int nranges = pick_ranges(args);
+    bp.nranges = (uint32_t)nranges;
+    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        k_probe_compact<<<g.sms * 2, kProbeThreads, (1 + 1024) * 4 + kProbeTile * 8, g.stream>>>(
+            g.inS.as<uint2>(), nS, bp, g.d_crc, g.sc.as<uint2>(), &ctrl->survivors, g.histS.as<uint32_t>(), 0u);
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    if (survivors_out && cnt) CK(cudaMemcpy(survivors_out, g.sc.p, cnt * 8, cudaMemcpyDeviceToHost));
+    CK(cudaGetLastError());
+    return (int64_t)cnt;
+}
+
+int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out, uint64_t* offsets) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (bits < 0 || bits > kMaxRadixBits || n >= (1ull << 32)) return -1;
+    ensure_workspace(n, 1, nullptr);
+    g.inR.ensure(std::max<uint64_t>(n, 2) * 8);
+    const uint32_t P = 1u << bits;
+    const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
+    h2d(g.inR.p, in, n * 8);
+    CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
+    BloomParams bp;
+    memset(&bp, 0, sizeof(bp));
+    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + 1024) * 4), g.stream>>>(g.inR.as<uint2>(), n, bp, g.d_crc,
+                                                                            g.histR.as<uint32_t>(), P - 1u);
+    int launches = 0;
+    const uint2* res = run_partition(g.inR.as<uint2>(), n, nullptr, bits, b2, g.histR.as<uint32_t>(),
+                                     g.offR.as<uint32_t>(), g.rt1.as<uint2>(), g.rp.as<uint2>(), launches);
+    std::vector<uint32_t> off32(P + 1);
+    if (n) CK(cudaMemcpyAsync(out, res, n * 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(off32.data(), g.offR.p, (P + 1) * 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    for (uint32_t i = 0; i <= P; i++) offsets[i] = off32[i];
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- multi-GPU (placeholder until the sharded pipeline lands) ----------------------------------------------------
+extern "C" {
+int hwbrj_dist_unique_id(void*) { return -1; }
+int hwbrj_dist_init(int, int, const void*, int) { return -1; }
+int hwbrj_dist_finalize(void) { return 0; }
+int hwbrj_join_device_dist(const hwbrj_rel_t*, const hwbrj_rel_t*, const bloom_filter_args_t*, hwbrj_stats_t*) { return -1; }
+}

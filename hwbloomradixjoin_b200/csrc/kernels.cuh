@@ -1,0 +1,608 @@
+// kernels.cuh -- the sm_100a kernels of the Bloom-filter radix join (K1..K5 of SURVEY.md 2.1).
+//
+// Data layout in HBM: relations are arrays of 8-byte {int32 key; int32 payload} tuples (types.h:37-40)
+// handled as uint2 (x = key, y = payload); the Bloom filter is m/32 uint32 words whose little-endian
+// byte/bit order equals the reference's byte array (bit b -> word b>>5, mask 1<<(b&31) == byte b>>3,
+// mask 1<<(b&7); bloom_filter.c:84,103).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "hash.cuh"
+
+namespace hwbrj {
+
+constexpr int kMaxLevelBits = 7;                     // radix bits per scatter pass
+constexpr int kMaxRadixBits = 2 * kMaxLevelBits;     // 2 passes
+constexpr int kTableCap = 8192;                      // R tuples per shared-memory hash table
+constexpr int kJoinThreads = 512;
+constexpr int kSChunk = 32768;                       // S tuples per join work item
+constexpr int kScatterThreads = 512;
+constexpr int kScatterTile = 4096;                   // tuples per scatter tile
+constexpr int kProbeThreads = 512;
+constexpr int kProbeV = 4;                           // 128-bit loads per thread per tile
+constexpr int kProbeTile = kProbeThreads * kProbeV * 2;
+
+struct BloomParams {
+    uint32_t* filter;      // m/32 words
+    uint32_t size_mask;    // (m-1) for BASIC, (B-1) for BLOCKED: modulus of the in-filter arithmetic
+    uint32_t nblocks_mask; // m/B - 1 (BLOCKED)
+    uint32_t log2B;        // log2(B) (BLOCKED)
+    uint32_t k;
+    uint32_t seed;
+    uint32_t blocked;
+    // range passes: a key is handled in the pass whose id equals (first bit address >> range_shift)
+    uint32_t nranges;
+    uint32_t range_shift;
+    uint32_t range_id;
+};
+
+struct JoinAccum {
+    unsigned long long matches, cpair, crpay, cspay, ckey;
+};
+
+__device__ __forceinline__ uint64_t mix64(uint32_t rpay, uint32_t spay) {
+    uint64_t z = ((uint64_t)rpay << 32) | (uint64_t)spay;
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+// streaming 128-bit load: read-once data must not displace the filter in L2
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const uint2* p, uint64_t pol) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// ---- Bloom index sequence (bloom_filter.c:74-111,126-141) ---------------------------------
+// first bit address, and the (h, y) state of the enhanced double hashing inside the (sub)filter
+__device__ __forceinline__ void bloom_start(const BloomParams& bp, const uint32_t* crc_tab, uint32_t key,
+                                            uint32_t& base, uint32_t& h, uint32_t& y) {
+    h = hash_crapwow(bp.seed, key) & bp.size_mask;
+    y = (key + bp.seed) & bp.size_mask;
+    base = bp.blocked ? ((crc32c_tab(crc_tab, bp.seed, key) & bp.nblocks_mask) << bp.log2B) : 0u;
+}
+__device__ __forceinline__ bool bloom_in_range(const BloomParams& bp, uint32_t addr0) {
+    return bp.nranges == 1u || (addr0 >> bp.range_shift) == bp.range_id;
+}
+
+__device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t base, uint32_t h, uint32_t y) {
+    for (uint32_t i = 0; i < bp.k; i++) {
+        uint32_t a = base + h;
+        atomicOr(bp.filter + (a >> 5), 1u << (a & 31u));  // RED.OR: relaxed, idempotent, order-free
+        h = (h + y) & bp.size_mask;
+        y = (y + i + 1u) & bp.size_mask;
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t* p) { return __ldg(p); }
+
+// probes 1..k-1 (the first word is passed in so that callers can batch the first probes)
+__device__ __forceinline__ bool bloom_test_rest(const BloomParams& bp, uint32_t base, uint32_t h, uint32_t y,
+                                                uint32_t w0) {
+    uint32_t a = base + h;
+    if (!((w0 >> (a & 31u)) & 1u)) return false;
+    for (uint32_t i = 1; i < bp.k; i++) {
+        h = (h + y) & bp.size_mask;
+        y = (y + i) & bp.size_mask;
+        a = base + h;
+        if (!((ld_filter(bp.filter + (a >> 5)) >> (a & 31u)) & 1u)) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void load_crc_tab(uint32_t* s_tab, const uint32_t* __restrict__ g_tab) {
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = g_tab[i];
+}
+
+// ---- K0: hash library entry ---------------------------------------------------------------------------------
+__global__ void k_hash_many(int which, uint32_t seed, const int32_t* __restrict__ keys, uint64_t n,
+                            uint32_t* __restrict__ out) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = hash_dispatch(which, seed, (uint32_t)keys[i]);
+}
+
+// ---- K1 (+K3 histogram): Bloom insert fused with the radix histogram of R ------------------------------------
+// replaces the build branch of the histogram loop, parallel_radix_join_bloom.c:794-805 + add_generic
+// (bloom_filter.c:74-89). Also used without a filter (plain PRO histogram, parallel_radix_join.c:770-775).
+// dynamic smem: hist[pmask+1] then crc table[1024]
+template <bool BLOOM>
+__global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ rel, uint64_t n, BloomParams bp,
+                                                    const uint32_t* __restrict__ g_crc, uint32_t* __restrict__ ghist,
+                                                    uint32_t pmask) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* hist = smem;
+    uint32_t* crc_tab = smem + (pmask + 1u);
+    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) hist[i] = 0u;
+    if (BLOOM && bp.blocked) load_crc_tab(crc_tab, g_crc);
+    __syncthreads();
+    const uint64_t pol = policy_evict_first();
+    const uint64_t npairs = n >> 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint4* rel4 = reinterpret_cast<const uint4*>(rel);
+    auto one = [&](uint32_t key) {
+        if (BLOOM) {
+            uint32_t base, h, y;
+            bloom_start(bp, crc_tab, key, base, h, y);
+            if (!bloom_in_range(bp, base + h)) return;
+            bloom_insert(bp, base, h, y);
+        }
+        atomicAdd(&hist[key & pmask], 1u);
+    };
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        uint4 v = ld_stream_v4(rel4 + i, pol);
+        one(v.x);
+        one(v.z);
+    }
+    if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) one(rel[n - 1].x);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) {
+        uint32_t c = hist[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// ---- K2: Bloom probe + ballot/prefix compaction of survivors + survivor histogram -----------------------------
+// replaces the probe branch of the histogram loop (:794-805), contains_generic (bloom_filter.c:93-111), the
+// contains_cache bitmap (:788,:801,:843) and the `filtered` sum (:1188-1193). Survivors are staged per CTA in
+// shared memory and flushed with one global cursor claim per tile (coalesced stores).
+// dynamic smem: stage[kProbeTile] uint2, hist[pmask+1], crc table[1024]
+__global__ void __launch_bounds__(kProbeThreads) k_probe_compact(const uint2* __restrict__ S, uint64_t n, BloomParams bp,
+                                                                const uint32_t* __restrict__ g_crc,
+                                                                uint2* __restrict__ out, unsigned long long* __restrict__ out_cursor,
+                                                                uint32_t* __restrict__ ghist, uint32_t pmask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* stage = reinterpret_cast<uint2*>(smem_raw);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + kProbeTile);
+    uint32_t* crc_tab = hist + (pmask + 1u);
+    __shared__ uint32_t s_count[2];  // double-buffered per tile parity: reset of one never races reads of the other
+    __shared__ unsigned long long s_gbase;
+    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) hist[i] = 0u;
+    if (bp.blocked) load_crc_tab(crc_tab, g_crc);
+    if (threadIdx.x == 0) s_count[0] = s_count[1] = 0u;
+    uint32_t par = 0u;
+    __syncthreads();
+    const uint64_t pol = policy_evict_first();
+    const uint64_t npairs = n >> 1;
+    const uint64_t ntiles = (npairs + kProbeThreads * kProbeV - 1) / (kProbeThreads * kProbeV);
+    const uint4* S4 = reinterpret_cast<const uint4*>(S);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t p0 = tile * (uint64_t)(kProbeThreads * kProbeV) + threadIdx.x;
+        uint4 t[kProbeV];
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            uint64_t idx = p0 + (uint64_t)j * kProbeThreads;
+            t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
+        bool act[2 * kProbeV];
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            bool valid = (p0 + (uint64_t)j * kProbeThreads) < npairs;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int q = 2 * j + e;
+                uint32_t key = e ? t[j].z : t[j].x;
+                bloom_start(bp, crc_tab, key, base[q], h[q], y[q]);
+                uint32_t a = base[q] + h[q];
+                act[q] = valid && bloom_in_range(bp, a);
+                w[q] = act[q] ? ld_filter(bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            bool fa = act[2 * j] && (bp.k == 0u || bloom_test_rest(bp, base[2 * j], h[2 * j], y[2 * j], w[2 * j]));
+            bool fb = act[2 * j + 1] &&
+                      (bp.k == 0u || bloom_test_rest(bp, base[2 * j + 1], h[2 * j + 1], y[2 * j + 1], w[2 * j + 1]));
+            uint32_t ma = __ballot_sync(0xffffffffu, fa);
+            uint32_t mb = __ballot_sync(0xffffffffu, fb);
+            uint32_t tot = __popc(ma) + __popc(mb);
+            uint32_t wbase = 0u;
+            if (tot) {
+                if (lane == 0) wbase = atomicAdd(&s_count[par], tot);
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (fa) {
+                    stage[wbase + __popc(ma & lt)] = make_uint2(t[j].x, t[j].y);
+                    atomicAdd(&hist[t[j].x & pmask], 1u);
+                }
+                if (fb) {
+                    stage[wbase + __popc(ma) + __popc(mb & lt)] = make_uint2(t[j].z, t[j].w);
+                    atomicAdd(&hist[t[j].z & pmask], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = s_count[par];
+        if (threadIdx.x == 0) {
+            s_gbase = cnt ? atomicAdd(out_cursor, (unsigned long long)cnt) : 0ull;
+            s_count[par ^ 1u] = 0u;
+        }
+        par ^= 1u;
+        __syncthreads();
+        const unsigned long long gb = s_gbase;
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) out[gb + i] = stage[i];
+        __syncthreads();
+    }
+    // odd tail tuple
+    if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint2 tt = S[n - 1];
+        uint32_t b0, h0, y0;
+        bloom_start(bp, crc_tab, tt.x, b0, h0, y0);
+        uint32_t a = b0 + h0;
+        if (bloom_in_range(bp, a) && (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp.filter + (a >> 5))))) {
+            unsigned long long pos = atomicAdd(out_cursor, 1ull);
+            out[pos] = tt;
+            atomicAdd(&hist[tt.x & pmask], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) {
+        uint32_t c = hist[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// ---- K3: exclusive scan of the partition histogram -------------------------------------------------------------
+// replaces the local prefix (:808-811) and the cross-thread offset computation (:819-837).
+// One CTA of 1024 threads; P <= 2^14. Produces fine_off[P+1], level-1 bucket cursors, level-2 cursors and the
+// tile schedule of the level-2 pass (tile_off[P1+1]).
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t P, uint32_t b2,
+                                              uint32_t* __restrict__ fine_off, uint32_t* __restrict__ cursor1,
+                                              uint32_t* __restrict__ cursor2, uint32_t* __restrict__ tile_off) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t s_tiles[(1 << kMaxLevelBits) + 1];
+    const uint32_t per = (P + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per;
+    uint32_t local = 0;
+    for (uint32_t i = 0; i < per; i++)
+        if (lo + i < P) local += hist[lo + i];
+    // block exclusive scan of `local`
+    uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t inc = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += v;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane];
+        uint32_t winc = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= (uint32_t)d) winc += v;
+        }
+        warp_sums[lane] = winc - ws;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + inc - local;
+    for (uint32_t i = 0; i < per; i++) {
+        uint32_t p = lo + i;
+        if (p < P) {
+            fine_off[p] = run;
+            cursor2[p] = run;
+            if ((p & ((1u << b2) - 1u)) == 0u) cursor1[p >> b2] = run;
+            run += hist[p];
+        }
+    }
+    if (threadIdx.x == 1023) fine_off[P] = run;  // thread 1023 owns the tail (or nothing): run == total
+    __syncthreads();
+    __threadfence_block();
+    // level-2 tile schedule: tiles per level-1 bucket
+    const uint32_t P1 = P >> b2;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t j = 0; j < P1; j++) {
+            s_tiles[j] = acc;
+            uint32_t nb = fine_off[(j + 1) << b2] - fine_off[j << b2];
+            acc += (nb + kScatterTile - 1) / kScatterTile;
+        }
+        s_tiles[P1] = acc;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j <= P1; j += blockDim.x) tile_off[j] = s_tiles[j];
+}
+
+// ---- K4: radix scatter with shared-memory staging ---------------------------------------------------------------
+// replaces the scatter loop (:842-849) and pass-2 radix_cluster (:574-608). Each CTA sorts a tile of
+// kScatterTile tuples by destination bin in shared memory (per-warp histograms -> ranks), claims one
+// contiguous range per non-empty bin from the global cursors, and writes every bin's run with coalesced stores.
+// LEVEL 1: input = whole relation, bin = pid >> b2, cursor index = bin.
+// LEVEL 2: input = level-1 output, work item = (bucket, tile) from tile_off, bin = pid & (2^b2-1),
+//          cursor index = pid.
+template <int LEVEL>
+__global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
+                                                            const uint64_t* __restrict__ n_ptr, uint64_t n_static,
+                                                            const uint32_t* __restrict__ fine_off,
+                                                            const uint32_t* __restrict__ tile_off,
+                                                            uint32_t* __restrict__ cursor, uint32_t pmask, uint32_t b2,
+                                                            uint32_t nbins) {
+    constexpr int NW = kScatterThreads / 32;
+    constexpr int PER = kScatterTile / kScatterThreads;
+    __shared__ __align__(16) uint2 sorted[kScatterTile];
+    __shared__ uint32_t whist[NW][1 << kMaxLevelBits];
+    __shared__ uint32_t binstart[1 << kMaxLevelBits];
+    __shared__ uint32_t gclaim[1 << kMaxLevelBits];
+    const uint32_t wid = threadIdx.x >> 5;
+    const uint64_t n = n_ptr ? *n_ptr : n_static;
+    const uint32_t P1 = (pmask + 1u) >> b2;
+    const uint64_t nitems = (LEVEL == 1) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
+    const uint32_t submask = (1u << b2) - 1u;
+    for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        uint64_t src0;
+        uint32_t cnt, cbase;
+        if (LEVEL == 1) {
+            src0 = item * kScatterTile;
+            cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
+            cbase = 0u;
+        } else {
+            // bucket j with tile_off[j] <= item < tile_off[j+1]
+            uint32_t lo = 0, hi = P1;
+            while (hi - lo > 1u) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (tile_off[mid] <= (uint32_t)item) lo = mid; else hi = mid;
+            }
+            uint32_t j = lo;
+            uint32_t bstart = fine_off[j << b2], bend = fine_off[(j + 1u) << b2];
+            uint32_t tl = (uint32_t)item - tile_off[j];
+            src0 = (uint64_t)bstart + (uint64_t)tl * kScatterTile;
+            cnt = min((uint32_t)kScatterTile, bend - (uint32_t)src0);
+            cbase = j << b2;
+        }
+        for (uint32_t i = threadIdx.x; i < NW * nbins; i += kScatterThreads) whist[i / nbins][i % nbins] = 0u;
+        __syncthreads();
+        uint2 t[PER];
+        uint32_t rank[PER];
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            uint32_t idx = threadIdx.x + j * kScatterThreads;
+            if (idx < cnt) {
+                t[j] = in[src0 + idx];
+                uint32_t pid = t[j].x & pmask;
+                uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
+                rank[j] = atomicAdd(&whist[wid][bin], 1u);
+            }
+        }
+        __syncthreads();
+        // per bin: turn per-warp counts into per-warp exclusive offsets, then scan the bin totals
+        uint32_t tot = 0;
+        if (threadIdx.x < nbins) {
+            for (int w = 0; w < NW; w++) {
+                uint32_t c = whist[w][threadIdx.x];
+                whist[w][threadIdx.x] = tot;
+                tot += c;
+            }
+            binstart[threadIdx.x] = tot;  // inclusive-scan input
+            gclaim[threadIdx.x] = tot ? atomicAdd(&cursor[cbase + threadIdx.x], tot) : 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // exclusive scan over nbins (<=128) totals: 4 per lane
+            uint32_t v[4], s = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t b = threadIdx.x * 4 + q;
+                v[q] = (b < nbins) ? binstart[b] : 0u;
+                s += v[q];
+            }
+            uint32_t inc = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((threadIdx.x & 31) >= d) inc += u;
+            }
+            uint32_t run = inc - s;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t b = threadIdx.x * 4 + q;
+                if (b < nbins) binstart[b] = run;
+                run += v[q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            uint32_t idx = threadIdx.x + j * kScatterThreads;
+            if (idx < cnt) {
+                uint32_t pid = t[j].x & pmask;
+                uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
+                sorted[binstart[bin] + whist[wid][bin] + rank[j]] = t[j];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
+            uint2 tt = sorted[i];
+            uint32_t pid = tt.x & pmask;
+            uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
+            out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = tt;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- join work list: one item per (partition, S chunk) --------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_worklist(const uint32_t* __restrict__ r_off, const uint32_t* __restrict__ s_off,
+                                                  uint32_t P, uint32_t* __restrict__ work_off) {
+    // single CTA, serial-per-thread chunks + block scan (P <= 16384)
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t per = (P + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per;
+    uint32_t local = 0;
+    for (uint32_t i = 0; i < per; i++) {
+        uint32_t p = lo + i;
+        if (p < P) {
+            uint32_t nr = r_off[p + 1] - r_off[p], ns = s_off[p + 1] - s_off[p];
+            local += (nr && ns) ? (ns + kSChunk - 1) / kSChunk : 0u;
+        }
+    }
+    uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t inc = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += v;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], winc = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= (uint32_t)d) winc += v;
+        }
+        warp_sums[lane] = winc - ws;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + inc - local;
+    for (uint32_t i = 0; i < per; i++) {
+        uint32_t p = lo + i;
+        if (p < P) {
+            work_off[p] = run;
+            uint32_t nr = r_off[p + 1] - r_off[p], ns = s_off[p + 1] - s_off[p];
+            run += (nr && ns) ? (ns + kSChunk - 1) / kSChunk : 0u;
+        }
+    }
+    if (threadIdx.x == 1023) work_off[P] = run;
+}
+
+// ---- K5: per-partition build + probe with the table in shared memory -----------------------------------------------
+// replaces bucket_chaining_join (:260-329): bucket heads + next links over the R partition held in shared
+// memory, idx = (key >> radix_bits) & (N-1) (HASH_BIT_MODULO with MASK=(N-1)<<bits), every equal key along the
+// chain counts. R partitions larger than kTableCap are processed in rounds; S partitions larger than kSChunk are
+// split over several work items (each rebuilds the table) so that skewed S does not serialise on one SM.
+__global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
+                                                      const uint2* __restrict__ Sp, const uint32_t* __restrict__ s_off,
+                                                      const uint32_t* __restrict__ work_off, uint32_t P, uint32_t bits,
+                                                      uint32_t* __restrict__ item_counter, JoinAccum* __restrict__ acc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* tab = reinterpret_cast<uint2*>(smem_raw);                  // kTableCap tuples
+    uint32_t* head = reinterpret_cast<uint32_t*>(tab + kTableCap);    // kTableCap heads (index+1, 0 = empty)
+    uint16_t* next = reinterpret_cast<uint16_t*>(head + kTableCap);   // kTableCap links
+    __shared__ uint32_t s_item;
+    __shared__ unsigned long long s_red[5][kJoinThreads / 32];
+    unsigned long long matches = 0, cpair = 0, crpay = 0, cspay = 0, ckey = 0;
+    const uint32_t total = work_off[P];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(item_counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= total) break;
+        uint32_t lo = 0, hi = P;
+        while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (work_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint32_t p = lo;
+        const uint32_t chunk = item - work_off[p];
+        const uint32_t r0 = r_off[p], nr = r_off[p + 1] - r0;
+        const uint32_t sbeg = s_off[p] + chunk * kSChunk;
+        const uint32_t send = min(s_off[p + 1], sbeg + (uint32_t)kSChunk);
+        for (uint32_t rb = 0; rb < nr; rb += kTableCap) {
+            const uint32_t cnt = min((uint32_t)kTableCap, nr - rb);
+            uint32_t N = 1u;
+            while (N < cnt) N <<= 1;
+            const uint32_t nmask = N - 1u;
+            if (rb) __syncthreads();
+            for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) head[i] = 0u;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < cnt; i += kJoinThreads) {
+                uint2 t = Rp[(uint64_t)r0 + rb + i];
+                tab[i] = t;
+                uint32_t idx = (t.x >> bits) & nmask;
+                next[i] = (uint16_t)atomicExch(&head[idx], i + 1u);
+            }
+            __syncthreads();
+            for (uint32_t i = sbeg + threadIdx.x; i < send; i += kJoinThreads) {
+                uint2 s = Sp[i];
+                uint32_t idx = (s.x >> bits) & nmask;
+                for (uint32_t hit = head[idx]; hit; hit = next[hit - 1u]) {
+                    uint2 r = tab[hit - 1u];
+                    if (r.x == s.x) {
+                        matches++;
+                        cpair += mix64(r.y, s.y);
+                        crpay += r.y;
+                        cspay += s.y;
+                        ckey += s.x;
+                    }
+                }
+            }
+        }
+    }
+    // block reduction
+    unsigned long long v[5] = {matches, cpair, crpay, cspay, ckey};
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], d);
+        if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        unsigned long long s = 0;
+        for (int w = 0; w < kJoinThreads / 32; w++) s += s_red[threadIdx.x][w];
+        if (s) atomicAdd(reinterpret_cast<unsigned long long*>(acc_out) + threadIdx.x, s);
+    }
+}
+
+// ---- on-device generator (SURVEY.md A.4 closed form of generator.c:162-195,341-387) ------------------------------
+// position permutation: 4-round Feistel over ceil(log2 n) bits with cycle walking (a bijection on [0,n))
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t x, uint64_t n, uint32_t half_bits, uint64_t seed) {
+    const uint64_t hmask = (1ull << half_bits) - 1ull;
+    do {
+        uint64_t l = x >> half_bits, r = x & hmask;
+#pragma unroll
+        for (int round = 0; round < 4; round++) {
+            uint64_t f = (r + seed + (uint64_t)round * 0x9e3779b97f4a7c15ULL) * 0xbf58476d1ce4e5b9ULL;
+            f ^= f >> 29;
+            f *= 0x94d049bb133111ebULL;
+            f ^= f >> 32;
+            uint64_t nl = r;
+            r = l ^ (f & hmask);
+            l = nl;
+        }
+        x = (l << half_bits) | r;
+    } while (x >= n);
+    return x;
+}
+
+// kind 0: R = permutation of 1..n, payload = position (main.c:430-431)
+// kind 1: S = nb keys ((e mod r)+1) and na keys r+1+e', payload = position (main.c:464-465)
+__global__ void k_generate(uint2* __restrict__ out, uint64_t n, int kind, uint64_t r, uint64_t nb, uint32_t half_bits,
+                           uint64_t seed) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t e = feistel_perm(i, n, half_bits, seed);
+        uint32_t key;
+        if (kind == 0) key = (uint32_t)(e + 1ull);
+        else if (e < nb) key = (uint32_t)(e % r + 1ull);
+        else {
+            uint64_t span = 2147483647ull - r;  // keys wrap back to r+1 after INT_MAX (generator.c:191-193)
+            key = (uint32_t)(r + 1ull + (e - nb) % (span ? span : 1ull));
+        }
+        out[i] = make_uint2(key, (uint32_t)i);
+    }
+}
+
+}  // namespace hwbrj

@@ -1,0 +1,198 @@
+/*
+ * hwbrj.h -- C ABI of libhwbrj_cuda.so: the B200 (sm_100a) drop-in for the reference's
+ * Bloom-filter radix hash join path.
+ *
+ * Part 1 is exactly what the reference's call site binds (main.c:277-282,331-339,473-478):
+ * the same type layouts (types.h:22-63, bloom_filter.h:10,50-55) and the same entry points
+ * (parallel_radix_join_bloom.h:34-86, parallel_radix_join.h:33-82). Part 2 are extensions the
+ * reference has no field for (filtered count, checksums, device timings, device-resident
+ * relations, multi-GPU bootstrap). Everything is extern "C" with plain pointers and sizes.
+ *
+ * There is no CPU fallback: every entry point runs CUDA kernels on the current device or fails
+ * loudly ([ERROR] ... + exit(EXIT_FAILURE), the reference's own error style,
+ * parallel_radix_join_bloom.c:64-71).
+ */
+#ifndef HWBRJ_H
+#define HWBRJ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* Part 1: the reference's ABI                                                                  */
+/* ------------------------------------------------------------------------------------------- */
+
+#ifndef TYPES_H /* do not clash when a host also includes the reference's types.h */
+#define TYPES_H
+typedef int32_t intkey_t; /* types.h:26-27 (KEY_8B off: 8-byte tuples) */
+typedef int32_t value_t;
+
+typedef struct tuple_t        tuple_t;
+typedef struct relation_t     relation_t;
+typedef struct result_t       result_t;
+typedef struct threadresult_t threadresult_t;
+
+struct tuple_t { /* types.h:37-40 */
+    intkey_t key;
+    value_t  payload;
+};
+
+struct relation_t { /* types.h:46-49 */
+    tuple_t * tuples;
+    uint64_t  num_tuples;
+};
+
+struct threadresult_t { /* types.h:52-56 */
+    int64_t  nresults;
+    void *   results;
+    uint32_t threadid;
+};
+
+struct result_t { /* types.h:59-63 */
+    int64_t          totalresults;
+    threadresult_t * resultlist;
+    int              nthreads;
+};
+#endif /* TYPES_H */
+
+#ifndef BLOOM_FILTER_H
+#define BLOOM_FILTER_H
+typedef enum { BASIC, BLOCKED } bloom_filter_variant_t; /* bloom_filter.h:10 */
+
+typedef struct bloom_filter_args_t { /* bloom_filter.h:50-55 */
+    bloom_filter_variant_t variant;
+    uint64_t               m; /* filter size in bits, power of two */
+    uint64_t               k; /* bits set per key */
+    uint64_t               B; /* block size in bits (BLOCKED), power of two, m % B == 0 */
+} bloom_filter_args_t;
+#endif /* BLOOM_FILTER_H */
+
+/*
+ * Join entry points. Same signatures and semantics as the reference: blocking; the caller owns
+ * relR/relS; the returned result_t is malloc()ed and the caller free()s it (main.c:490);
+ * totalresults = number of (r,s) pairs with equal keys. The Bloom variants print
+ * "S-tuples after filter: N" (BRJ does not, as in the reference) and all print the
+ * print_timing() block (parallel_radix_join_bloom.c:1510-1547) unless hwbrj_set_quiet(1).
+ * Unlike the reference the inputs are NOT modified and need no RELATION_PADDING slack.
+ * `nthreads` is accepted for signature compatibility; it is echoed in result_t.nthreads.
+ * BPRH/BPRHO/PRH/PRHO give the same results as BPRO/PRO and alias the same pipeline.
+ */
+result_t * BPRO(relation_t * relR, relation_t * relS, int nthreads, bloom_filter_args_t * args);  /* parallel_radix_join_bloom.c:1782 */
+result_t * BRJ(relation_t * relR, relation_t * relS, int nthreads, bloom_filter_args_t * args);   /* :1808 */
+result_t * BPRH(relation_t * relR, relation_t * relS, int nthreads, bloom_filter_args_t * args);  /* :1791 */
+result_t * BPRHO(relation_t * relR, relation_t * relS, int nthreads, bloom_filter_args_t * args); /* :1799 */
+result_t * PRO(relation_t * relR, relation_t * relS, int nthreads);                               /* parallel_radix_join.c:1697 */
+result_t * RJ(relation_t * relR, relation_t * relS, int nthreads);                                /* :1718 */
+result_t * PRH(relation_t * relR, relation_t * relS, int nthreads);
+result_t * PRHO(relation_t * relR, relation_t * relS, int nthreads);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Part 2: extensions                                                                           */
+/* ------------------------------------------------------------------------------------------- */
+
+/* pair mixer used by checksum_pair: splitmix64 finaliser over (R.payload << 32 | S.payload) */
+static inline uint64_t
+hwbrj_mix64(uint32_t rpay, uint32_t spay)
+{
+    uint64_t z = ((uint64_t) rpay << 32) | (uint64_t) spay;
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+typedef struct hwbrj_stats_t {
+    int64_t  matches;       /* = result_t.totalresults */
+    int64_t  filtered;      /* S tuples passing the filter; -1 when no filter was used */
+    uint64_t checksum_pair; /* sum over output pairs of hwbrj_mix64(R.payload,S.payload) mod 2^64 */
+    uint64_t checksum_rpay; /* sum over output pairs of (uint32)R.payload */
+    uint64_t checksum_spay; /* sum over output pairs of (uint32)S.payload */
+    uint64_t checksum_key;  /* sum over output pairs of (uint32)S.key */
+    /* device timings, CUDA events on the library's stream, milliseconds */
+    float    ms_total;      /* whole join, inputs resident, filter zeroing excluded (reference timing region) */
+    float    ms_memset;     /* zero-fill of the filter and scratch (excluded from ms_total, as :1583 is) */
+    float    ms_build;      /* R: Bloom insert + histogram */
+    float    ms_part_r;     /* R: scatter passes */
+    float    ms_probe;      /* S: Bloom probe + compaction + histogram */
+    float    ms_part_s;     /* S: scatter passes */
+    float    ms_join;       /* per-partition build + probe */
+    float    ms_h2d;        /* host->device copies (host-buffer entry points only) */
+    float    ms_e2e;        /* wall clock of the whole host-buffer call, incl. copies */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    int32_t  kernel_launches; /* kernels launched inside the timed region */
+    int32_t  radix_bits;      /* total radix bits used */
+    int32_t  range_passes;    /* filter range passes used by insert/probe */
+    int32_t  n_gpus;
+    float    ms_comm;         /* multi-GPU: time in collectives */
+    float    reserved[3];
+} hwbrj_stats_t;
+
+/* results of the most recent join in this process */
+int      hwbrj_last_stats(hwbrj_stats_t * out);
+int64_t  hwbrj_last_filtered(void);
+uint64_t hwbrj_last_checksum(void); /* checksum_pair */
+
+void hwbrj_set_quiet(int quiet);    /* 1: suppress the reference-style stdout lines */
+/* tuning knobs (also read from env HWBRJ_RADIX_BITS / HWBRJ_RANGE_PASSES); 0 = automatic */
+void hwbrj_set_radix_bits(int bits);
+void hwbrj_set_range_passes(int passes);
+const char * hwbrj_version(void);
+int  hwbrj_device_count(void);
+
+/* argument validation with the reference's rules (bloom_filter.c:26-34); returns 0 when valid,
+ * else prints the reference's message and returns non-zero (the reference exits) */
+int hwbrj_check_args(const bloom_filter_args_t * args);
+
+/* ---- device-resident relations (inputs already in HBM: the timing region of `value`) ------- */
+typedef struct hwbrj_rel hwbrj_rel_t; /* opaque device relation */
+
+hwbrj_rel_t * hwbrj_rel_upload(const tuple_t * tuples, uint64_t n);
+/* on-device generator with the reference generator's key multiset (generator.c:162-195,341-387):
+ * kind 0: R = keys 1..n (payload = position); kind 1: S = FK relation over threshold r with selectivity q.
+ * Positions are permuted by a seeded bijection (the reference's own shuffle is time-seeded). */
+hwbrj_rel_t * hwbrj_rel_generate(int kind, uint64_t n, uint64_t r, double q, uint64_t seed);
+int      hwbrj_rel_download(const hwbrj_rel_t * rel, tuple_t * out);
+uint64_t hwbrj_rel_size(const hwbrj_rel_t * rel);
+void     hwbrj_rel_free(hwbrj_rel_t * rel);
+
+/* join of device-resident relations; args == NULL -> plain radix join (PRO). Returns 0 on success. */
+int hwbrj_join_device(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
+                      hwbrj_stats_t * out);
+
+/* pinned host buffers for callers that want full-speed PCIe copies (bench e2e leg) */
+void * hwbrj_host_alloc(uint64_t bytes);
+void   hwbrj_host_free(void * p);
+
+/* ---- building blocks, exposed for parity tests --------------------------------------------- */
+/* which: 0 crc,1 FNV,2 crapwow,3 Coffin,4 MurmurOAAT,5 JenkinsOAAT,6 Spooky,7 KR_v2,8 DJB2,9 x17 (hash.h:12-40) */
+int hwbrj_hash_many(int which, uint32_t seed, const int32_t * keys, uint64_t n, uint32_t * out);
+/* build the filter on the GPU from R's keys and copy the m/8-byte bitmap back (bloom_filter.c:74-89,126-132) */
+int hwbrj_bloom_build(const tuple_t * R, uint64_t nR, const bloom_filter_args_t * args, uint32_t seed,
+                      unsigned char * bitmap_out);
+/* probe S against a given bitmap on the GPU; returns the pass count, optionally the survivors
+ * (any order) and their number (bloom_filter.c:93-111,135-141) */
+int64_t hwbrj_bloom_probe(const unsigned char * bitmap, const tuple_t * S, uint64_t nS,
+                          const bloom_filter_args_t * args, uint32_t seed, tuple_t * survivors_out);
+/* radix-partition a relation on the GPU with the pipeline's own kernels: out receives the tuples
+ * grouped by (key & (2^bits-1)) in increasing partition order, offsets (2^bits+1 entries) the
+ * partition boundaries (parallel_radix_join_bloom.c:574-608,759-852 equivalent) */
+int hwbrj_radix_partition(const tuple_t * in, uint64_t n, int bits, tuple_t * out, uint64_t * offsets);
+
+/* ---- multi-GPU (one process per GPU, NCCL bootstrap through the host's own channel) --------- */
+#define HWBRJ_NCCL_ID_BYTES 128
+int hwbrj_dist_unique_id(void * id_out /* HWBRJ_NCCL_ID_BYTES */);
+int hwbrj_dist_init(int rank, int world, const void * id, int local_device);
+int hwbrj_dist_finalize(void);
+/* collective join: every rank passes its local shard of R and S (device-resident); the scalars in
+ * `out` are the all-reduced global results, identical on every rank. */
+int hwbrj_join_device_dist(const hwbrj_rel_t * Rshard, const hwbrj_rel_t * Sshard,
+                           const bloom_filter_args_t * args, hwbrj_stats_t * out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HWBRJ_H */
