@@ -83,6 +83,8 @@ struct Ctx {
     bool quiet = false;
     int radix_bits_override = 0;
     int range_passes_override = 0;
+    int probe_ctas_per_sm = 0;  // 0 = occupancy API
+    int occ_probe = 1, occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
     std::mutex mu;
 };
 
@@ -108,12 +110,21 @@ static void init_ctx() {
     const int hist_smem = ((1 << kMaxRadixBits) + 1024) * 4;
     CK(cudaFuncSetAttribute(k_build_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    CK(cudaFuncSetAttribute(k_probe_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            hist_smem + kProbeTile * 8));
     CK(cudaFuncSetAttribute(k_join, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
     if (const char* s = getenv("HWBRJ_RADIX_BITS")) g.radix_bits_override = atoi(s);
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
+    if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_probe, k_probe_compact<7>, kProbeWarps * 32, 0));
+    CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter1, k_scatter<1>, kScatterThreads, kScatterSmem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter2, k_scatter<2>, kScatterThreads, kScatterSmem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join, kJoinThreads, kTableCap * (8 + 4 + 2)));
+    g.occ_probe = std::max(g.occ_probe, 1);
+    g.occ_scatter1 = std::max(g.occ_scatter1, 1);
+    g.occ_scatter2 = std::max(g.occ_scatter2, 1);
+    g.occ_join = std::max(g.occ_join, 1);
     memset(&g.last, 0, sizeof(g.last));
     g.inited = true;
 }
@@ -190,6 +201,29 @@ static int pick_bits(uint64_t nR) {
     return b;
 }
 
+
+// K2 launch with compile-time specialisation on (blocked, k == 1, ranged)
+static void launch_probe(const uint2* dS, uint64_t nS, const BloomParams& bp, uint2* out, unsigned long long* cursor) {
+    const int mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0) | (bp.nranges > 1u ? 4 : 0);
+    static int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HWBRJ_PROBE_CASE(M)                                                                                        \
+    case M: {                                                                                                      \
+        if (!occ[M]) {                                                                                             \
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[M], k_probe_compact<M>, kProbeWarps * 32, 0));   \
+            occ[M] = std::max(occ[M], 1);                                                                          \
+        }                                                                                                          \
+        /* measured on B200: 4 CTAs/SM beats the occupancy maximum (less L2 thrash of the filter range) */ \
+        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(occ[M], 4));                             \
+        k_probe_compact<M><<<grid, kProbeWarps * 32, 0, g.stream>>>(dS, nS, bp, g.d_crc, out, cursor);            \
+        break;                                                                                                     \
+    }
+    switch (mode) {
+        HWBRJ_PROBE_CASE(0) HWBRJ_PROBE_CASE(1) HWBRJ_PROBE_CASE(2) HWBRJ_PROBE_CASE(3)
+        HWBRJ_PROBE_CASE(4) HWBRJ_PROBE_CASE(5) HWBRJ_PROBE_CASE(6) HWBRJ_PROBE_CASE(7)
+    }
+#undef HWBRJ_PROBE_CASE
+}
+
 struct Partitioned {
     const uint2* data;
     const uint32_t* off;
@@ -204,13 +238,12 @@ static const uint2* run_partition(const uint2* in, uint64_t n, const unsigned lo
     k_scan<<<1, 1024, 0, g.stream>>>(hist, P, (uint32_t)b2, off, g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(),
                                      g.tiles.as<uint32_t>());
     launches++;
-    const int grid = g.sms * 4;
-    k_scatter<1><<<grid, kScatterThreads, 0, g.stream>>>(in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off,
+    k_scatter<1><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off,
                                                         g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pmask,
                                                         (uint32_t)b2, 1u << b1);
     launches++;
     if (b2 == 0) return t1;
-    k_scatter<2><<<grid, kScatterThreads, 0, g.stream>>>(t1, t2, nullptr, n, off, g.tiles.as<uint32_t>(),
+    k_scatter<2><<<g.sms * g.occ_scatter2, kScatterThreads, kScatterSmem, g.stream>>>(t1, t2, nullptr, n, off, g.tiles.as<uint32_t>(),
                                                         g.cur2.as<uint32_t>(), pmask, (uint32_t)b2, 1u << b2);
     launches++;
     return t2;
@@ -268,11 +301,11 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
         for (int r = 0; r < nranges; r++) {
             bp.range_id = (uint32_t)r;
-            k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+            k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nullptr, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
             launches++;
         }
     } else {
-        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nullptr, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
         launches++;
     }
     CK(cudaEventRecord(g.ev[2], g.stream));
@@ -282,19 +315,17 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     const uint2* Sin = dS;
     const unsigned long long* n_dev = nullptr;
     if (args) {
-        const int probe_smem = hist_smem + kProbeTile * 8;
         for (int r = 0; r < nranges; r++) {
             bp.range_id = (uint32_t)r;
-            k_probe_compact<<<g.sms * 2, kProbeThreads, probe_smem, g.stream>>>(
-                dS, nS, bp, g.d_crc, g.sc.as<uint2>(), &ctrl->survivors, g.histS.as<uint32_t>(), pmask);
+            launch_probe(dS, nS, bp, g.sc.as<uint2>(), &ctrl->survivors);
             launches++;
         }
         Sin = g.sc.as<uint2>();
         n_dev = &ctrl->survivors;
-    } else {
-        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dS, nS, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
-        launches++;
     }
+    // radix histogram of the tuples that go on to the join (survivors, or all of S without a filter)
+    k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
+    launches++;
     CK(cudaEventRecord(g.ev[4], g.stream));
     // with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc
     const uint2* Sp = run_partition(Sin, nS, n_dev, bits, b2, g.histS.as<uint32_t>(), g.offS.as<uint32_t>(),
@@ -302,7 +333,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     CK(cudaEventRecord(g.ev[5], g.stream));
     k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>());
     launches++;
-    k_join<<<g.sms * 2, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
+    k_join<<<g.sms * g.occ_join, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
         Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
         &ctrl->item_counter, &ctrl->acc);
     launches++;
@@ -461,7 +492,7 @@ hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
     init_ctx();
     hwbrj_rel_t* r = new hwbrj_rel;
     r->n = n;
-    CK(cudaMalloc(&r->d, std::max<uint64_t>(n, 2) * 8));
+    CK(cudaMalloc(&r->d, std::max<uint64_t>(n, 2) * 8 + 64));
     if (n) CK(cudaMemcpy(r->d, tuples, n * 8, cudaMemcpyHostToDevice));
     return r;
 }
@@ -471,7 +502,7 @@ hwbrj_rel_t* hwbrj_rel_generate(int kind, uint64_t n, uint64_t r, double q, uint
     init_ctx();
     hwbrj_rel_t* rel = new hwbrj_rel;
     rel->n = n;
-    CK(cudaMalloc(&rel->d, std::max<uint64_t>(n, 2) * 8));
+    CK(cudaMalloc(&rel->d, std::max<uint64_t>(n, 2) * 8 + 64));
     if (n) {
         // generator.c:344: ntuples_above = num_tuples * (1 - selectivity)
         uint64_t na = kind == 1 ? (uint64_t)((double)n * (1.0 - q)) : 0;
@@ -553,7 +584,7 @@ int hwbrj_bloom_build(const tuple_t* R, uint64_t nR, const bloom_filter_args_t* 
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + 1024) * 4, g.stream>>>(g.inR.as<uint2>(), nR, bp, g.d_crc,
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + 1024) * 4, g.stream>>>(g.inR.as<uint2>(), nR, nullptr, bp, g.d_crc,
                                                                           g.histR.as<uint32_t>(), 0u);
     }
     CK(cudaMemcpyAsync(bitmap_out, g.filter.p, args->m / 8, cudaMemcpyDeviceToHost, g.stream));
@@ -583,8 +614,7 @@ int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_probe_compact<<<g.sms * 2, kProbeThreads, (1 + 1024) * 4 + kProbeTile * 8, g.stream>>>(
-            g.inS.as<uint2>(), nS, bp, g.d_crc, g.sc.as<uint2>(), &ctrl->survivors, g.histS.as<uint32_t>(), 0u);
+        launch_probe(g.inS.as<uint2>(), nS, bp, g.sc.as<uint2>(), &ctrl->survivors);
     }
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
@@ -606,7 +636,7 @@ int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out,
     CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
-    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + 1024) * 4), g.stream>>>(g.inR.as<uint2>(), n, bp, g.d_crc,
+    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + 1024) * 4), g.stream>>>(g.inR.as<uint2>(), n, nullptr, bp, g.d_crc,
                                                                             g.histR.as<uint32_t>(), P - 1u);
     int launches = 0;
     const uint2* res = run_partition(g.inR.as<uint2>(), n, nullptr, bits, b2, g.histR.as<uint32_t>(),

@@ -16,11 +16,12 @@ constexpr int kMaxRadixBits = 2 * kMaxLevelBits;     // 2 passes
 constexpr int kTableCap = 8192;                      // R tuples per shared-memory hash table
 constexpr int kJoinThreads = 512;
 constexpr int kSChunk = 32768;                       // S tuples per join work item
-constexpr int kScatterThreads = 512;
-constexpr int kScatterTile = 4096;                   // tuples per scatter tile
-constexpr int kProbeThreads = 512;
-constexpr int kProbeV = 4;                           // 128-bit loads per thread per tile
-constexpr int kProbeTile = kProbeThreads * kProbeV * 2;
+constexpr int kScatterThreads = 256;
+constexpr int kScatterTile = 2048;                   // tuples per scatter tile
+constexpr int kScatterStages = 3;                    // TMA bulk-load ring depth
+constexpr int kScatterStageTuples = kScatterTile + 2; // +1 misaligned head, +1 rounding to 16 bytes
+constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTile) * 8;
+constexpr int kProbeV = 4;                           // 128-bit loads in flight per lane in K2
 
 struct BloomParams {
     uint32_t* filter;      // m/32 words
@@ -63,10 +64,40 @@ __device__ __forceinline__ uint2 ld_stream_v2(const uint2* p, uint64_t pol) {
                  : "l"(p), "l"(pol));
     return r;
 }
+__device__ __forceinline__ void st_stream_v2(uint2* p, uint2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
+}
+
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy; src and dst 16-byte aligned, bytes a multiple of 16; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // ---- Bloom index sequence (bloom_filter.c:74-111,126-141) ---------------------------------
@@ -123,10 +154,12 @@ __global__ void k_hash_many(int which, uint32_t seed, const int32_t* __restrict_
 // (bloom_filter.c:74-89). Also used without a filter (plain PRO histogram, parallel_radix_join.c:770-775).
 // dynamic smem: hist[pmask+1] then crc table[1024]
 template <bool BLOOM>
-__global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ rel, uint64_t n, BloomParams bp,
+__global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ rel, uint64_t n_static,
+                                                    const unsigned long long* __restrict__ n_ptr, BloomParams bp,
                                                     const uint32_t* __restrict__ g_crc, uint32_t* __restrict__ ghist,
                                                     uint32_t pmask) {
     extern __shared__ uint32_t smem[];
+    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
     uint32_t* hist = smem;
     uint32_t* crc_tab = smem + (pmask + 1u);
     for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) hist[i] = 0u;
@@ -158,45 +191,68 @@ __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ r
     }
 }
 
-// ---- K2: Bloom probe + ballot/prefix compaction of survivors + survivor histogram -----------------------------
+// ---- K2: Bloom probe + ballot/prefix compaction of survivors ----------------------------------------------------
 // replaces the probe branch of the histogram loop (:794-805), contains_generic (bloom_filter.c:93-111), the
-// contains_cache bitmap (:788,:801,:843) and the `filtered` sum (:1188-1193). Survivors are staged per CTA in
-// shared memory and flushed with one global cursor claim per tile (coalesced stores).
-// dynamic smem: stage[kProbeTile] uint2, hist[pmask+1], crc table[1024]
-__global__ void __launch_bounds__(kProbeThreads) k_probe_compact(const uint2* __restrict__ S, uint64_t n, BloomParams bp,
-                                                                const uint32_t* __restrict__ g_crc,
-                                                                uint2* __restrict__ out, unsigned long long* __restrict__ out_cursor,
-                                                                uint32_t* __restrict__ ghist, uint32_t pmask) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2* stage = reinterpret_cast<uint2*>(smem_raw);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + kProbeTile);
-    uint32_t* crc_tab = hist + (pmask + 1u);
-    __shared__ uint32_t s_count[2];  // double-buffered per tile parity: reset of one never races reads of the other
-    __shared__ unsigned long long s_gbase;
-    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) hist[i] = 0u;
-    if (bp.blocked) load_crc_tab(crc_tab, g_crc);
-    if (threadIdx.x == 0) s_count[0] = s_count[1] = 0u;
-    uint32_t par = 0u;
-    __syncthreads();
+// contains_cache bitmap (:788,:801,:843) and the `filtered` sum (:1188-1193).
+// Warp-autonomous: no block barrier in the streaming loop, so loads of different warps stay in flight while
+// others compact. Each warp streams 32 x kProbeV 128-bit loads (2 tuples each), issues all first probes
+// together, and appends survivors to its private shared-memory ring; whenever the ring holds kWarpFlush
+// tuples the warp claims kWarpFlush slots of the output with ONE global atomic and writes them as whole
+// 128-byte lines (claims are multiples of kWarpFlush, so every flush but the last is line-aligned).
+constexpr int kWarpFlush = 256;              // tuples per flush (2 KB)
+constexpr int kWarpRing = 2 * kWarpFlush;    // ring capacity per warp (power of two)
+constexpr int kProbeWarps = 8;               // warps per CTA
+// MODE bit0: BLOCKED, bit1: single probe (k == 1), bit2: range passes active -- compile-time specialisation keeps
+// the per-tuple instruction count down (the kernel is issue- and L1TEX-wavefront-bound, not HBM-bound).
+template <int MODE>
+__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2* __restrict__ S, uint64_t n, BloomParams bp_in,
+                                                                   const uint32_t* __restrict__ g_crc,
+                                                                   uint2* __restrict__ out,
+                                                                   unsigned long long* __restrict__ out_cursor) {
+    constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0;
+    __shared__ __align__(16) uint2 ring_all[kProbeWarps][kWarpRing];
+    __shared__ uint32_t crc_tab[kBlocked ? 1024 : 1];
+    BloomParams bp = bp_in;
+    bp.blocked = kBlocked ? 1u : 0u;
+    if (kSingle) bp.k = 1u;
+    if (!kRanged) bp.nranges = 1u;
+    if (kBlocked) {
+        load_crc_tab(crc_tab, g_crc);
+        __syncthreads();
+    }
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2* ring = ring_all[wid];
+    uint32_t head = 0u, count = 0u;  // warp-uniform ring state (tail = head + count)
     const uint64_t pol = policy_evict_first();
     const uint64_t npairs = n >> 1;
-    const uint64_t ntiles = (npairs + kProbeThreads * kProbeV - 1) / (kProbeThreads * kProbeV);
     const uint4* S4 = reinterpret_cast<const uint4*>(S);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t p0 = tile * (uint64_t)(kProbeThreads * kProbeV) + threadIdx.x;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kProbeWarps + wid;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
+    constexpr uint64_t kPerIter = 32ull * kProbeV;  // pairs per warp iteration
+
+    auto flush = [&](uint32_t cnt) {
+        unsigned long long gb = 0ull;
+        if (lane == 0) gb = atomicAdd(out_cursor, (unsigned long long)cnt);
+        gb = __shfl_sync(0xffffffffu, gb, 0);
+        for (uint32_t i = lane; i < cnt; i += 32u) st_stream_v2(out + gb + i, ring[(head + i) & (kWarpRing - 1)], pol);
+        head = (head + cnt) & (kWarpRing - 1);
+        count -= cnt;
+    };
+
+    for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
+        const uint64_t p0 = it * kPerIter + lane;
         uint4 t[kProbeV];
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
-            uint64_t idx = p0 + (uint64_t)j * kProbeThreads;
+            uint64_t idx = p0 + (uint64_t)j * 32u;
             t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
         }
         uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
         bool act[2 * kProbeV];
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
-            bool valid = (p0 + (uint64_t)j * kProbeThreads) < npairs;
+            bool valid = (p0 + (uint64_t)j * 32u) < npairs;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int q = 2 * j + e;
@@ -214,33 +270,16 @@ __global__ void __launch_bounds__(kProbeThreads) k_probe_compact(const uint2* __
                       (bp.k == 0u || bloom_test_rest(bp, base[2 * j + 1], h[2 * j + 1], y[2 * j + 1], w[2 * j + 1]));
             uint32_t ma = __ballot_sync(0xffffffffu, fa);
             uint32_t mb = __ballot_sync(0xffffffffu, fb);
-            uint32_t tot = __popc(ma) + __popc(mb);
-            uint32_t wbase = 0u;
-            if (tot) {
-                if (lane == 0) wbase = atomicAdd(&s_count[par], tot);
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (fa) {
-                    stage[wbase + __popc(ma & lt)] = make_uint2(t[j].x, t[j].y);
-                    atomicAdd(&hist[t[j].x & pmask], 1u);
-                }
-                if (fb) {
-                    stage[wbase + __popc(ma) + __popc(mb & lt)] = make_uint2(t[j].z, t[j].w);
-                    atomicAdd(&hist[t[j].z & pmask], 1u);
-                }
-            }
+            uint32_t tail = head + count;
+            if (fa) ring[(tail + __popc(ma & lt)) & (kWarpRing - 1)] = make_uint2(t[j].x, t[j].y);
+            if (fb) ring[(tail + __popc(ma) + __popc(mb & lt)) & (kWarpRing - 1)] = make_uint2(t[j].z, t[j].w);
+            count += __popc(ma) + __popc(mb);
+            __syncwarp();
+            if (count >= (uint32_t)kWarpFlush) flush(kWarpFlush);  // <= 64 appended per step, ring never overflows
         }
-        __syncthreads();
-        const uint32_t cnt = s_count[par];
-        if (threadIdx.x == 0) {
-            s_gbase = cnt ? atomicAdd(out_cursor, (unsigned long long)cnt) : 0ull;
-            s_count[par ^ 1u] = 0u;
-        }
-        par ^= 1u;
-        __syncthreads();
-        const unsigned long long gb = s_gbase;
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) out[gb + i] = stage[i];
-        __syncthreads();
     }
+    __syncwarp();
+    if (count) flush(count);
     // odd tail tuple
     if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {
         uint2 tt = S[n - 1];
@@ -250,13 +289,7 @@ __global__ void __launch_bounds__(kProbeThreads) k_probe_compact(const uint2* __
         if (bloom_in_range(bp, a) && (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp.filter + (a >> 5))))) {
             unsigned long long pos = atomicAdd(out_cursor, 1ull);
             out[pos] = tt;
-            atomicAdd(&hist[tt.x & pmask], 1u);
         }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) {
-        uint32_t c = hist[i];
-        if (c) atomicAdd(&ghist[i], c);
     }
 }
 
@@ -324,12 +357,48 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist
 }
 
 // ---- K4: radix scatter with shared-memory staging ---------------------------------------------------------------
-// replaces the scatter loop (:842-849) and pass-2 radix_cluster (:574-608). Each CTA sorts a tile of
-// kScatterTile tuples by destination bin in shared memory (per-warp histograms -> ranks), claims one
-// contiguous range per non-empty bin from the global cursors, and writes every bin's run with coalesced stores.
+// replaces the scatter loop (:842-849) and pass-2 radix_cluster (:574-608).
+// Persistent CTAs; every CTA walks its tiles of kScatterTile tuples through a kScatterStages-deep ring of TMA
+// bulk loads (cp.async.bulk -> mbarrier), so the HBM read of the next tiles is in flight while the current tile
+// is sorted by destination bin in shared memory (per-warp histograms -> ranks), claims one contiguous range per
+// non-empty bin from the global cursors and writes every bin's run with coalesced stores.
 // LEVEL 1: input = whole relation, bin = pid >> b2, cursor index = bin.
 // LEVEL 2: input = level-1 output, work item = (bucket, tile) from tile_off, bin = pid & (2^b2-1),
 //          cursor index = pid.
+struct ScatterItem {
+    uint64_t src_al;   // first tuple index of the bulk load (even: 16-byte aligned)
+    uint32_t skip;     // 0/1 tuples to skip at the head of the staged tile
+    uint32_t cnt;      // tuples of this tile
+    uint32_t cbase;    // cursor base index
+    uint32_t bytes;    // bulk-load size
+};
+
+template <int LEVEL>
+__device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ fine_off,
+                                                    const uint32_t* __restrict__ tile_off, uint32_t P1, uint32_t b2) {
+    ScatterItem it;
+    uint64_t src0;
+    if (LEVEL == 1) {
+        src0 = item * kScatterTile;
+        it.cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
+        it.cbase = 0u;
+    } else {
+        uint32_t lo = 0, hi = P1;  // bucket j with tile_off[j] <= item < tile_off[j+1]
+        while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (tile_off[mid] <= (uint32_t)item) lo = mid; else hi = mid;
+        }
+        uint32_t bstart = fine_off[lo << b2], bend = fine_off[(lo + 1u) << b2];
+        src0 = (uint64_t)bstart + (uint64_t)((uint32_t)item - tile_off[lo]) * kScatterTile;
+        it.cnt = min((uint32_t)kScatterTile, bend - (uint32_t)src0);
+        it.cbase = lo << b2;
+    }
+    it.skip = (uint32_t)(src0 & 1ull);
+    it.src_al = src0 - it.skip;
+    it.bytes = ((it.cnt + it.skip + 1u) & ~1u) * 8u;
+    return it;
+}
+
 template <int LEVEL>
 __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
                                                             const uint64_t* __restrict__ n_ptr, uint64_t n_static,
@@ -339,87 +408,98 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __rest
                                                             uint32_t nbins) {
     constexpr int NW = kScatterThreads / 32;
     constexpr int PER = kScatterTile / kScatterThreads;
-    __shared__ __align__(16) uint2 sorted[kScatterTile];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2* raw = reinterpret_cast<uint2*>(smem_raw);                       // [stages][kScatterStageTuples]
+    uint2* sorted = raw + kScatterStages * kScatterStageTuples;            // [kScatterTile]
     __shared__ uint32_t whist[NW][1 << kMaxLevelBits];
     __shared__ uint32_t binstart[1 << kMaxLevelBits];
     __shared__ uint32_t gclaim[1 << kMaxLevelBits];
+    __shared__ __align__(8) uint64_t mbar[kScatterStages];
+    __shared__ ScatterItem desc[kScatterStages];
     const uint32_t wid = threadIdx.x >> 5;
     const uint64_t n = n_ptr ? *n_ptr : n_static;
     const uint32_t P1 = (pmask + 1u) >> b2;
     const uint64_t nitems = (LEVEL == 1) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
     const uint32_t submask = (1u << b2) - 1u;
-    for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        uint64_t src0;
-        uint32_t cnt, cbase;
-        if (LEVEL == 1) {
-            src0 = item * kScatterTile;
-            cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
-            cbase = 0u;
-        } else {
-            // bucket j with tile_off[j] <= item < tile_off[j+1]
-            uint32_t lo = 0, hi = P1;
-            while (hi - lo > 1u) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (tile_off[mid] <= (uint32_t)item) lo = mid; else hi = mid;
-            }
-            uint32_t j = lo;
-            uint32_t bstart = fine_off[j << b2], bend = fine_off[(j + 1u) << b2];
-            uint32_t tl = (uint32_t)item - tile_off[j];
-            src0 = (uint64_t)bstart + (uint64_t)tl * kScatterTile;
-            cnt = min((uint32_t)kScatterTile, bend - (uint32_t)src0);
-            cbase = j << b2;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t item, int st) {  // thread 0 only
+        ScatterItem it = scatter_item<LEVEL>(item, n, fine_off, tile_off, P1, b2);
+        desc[st] = it;
+        mbar_arrive_expect_tx(&mbar[st], it.bytes);
+        bulk_g2s(raw + st * kScatterStageTuples, in + it.src_al, it.bytes, &mbar[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int st = 0; st < kScatterStages; st++) {
+            uint64_t item = (uint64_t)blockIdx.x + (uint64_t)st * gridDim.x;
+            if (item < nitems) issue(item, st);
         }
+    uint32_t it_local = 0;
+    for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x, it_local++) {
+        const int st = it_local % kScatterStages;
+        const uint32_t parity = (it_local / kScatterStages) & 1u;
         for (uint32_t i = threadIdx.x; i < NW * nbins; i += kScatterThreads) whist[i / nbins][i % nbins] = 0u;
-        __syncthreads();
+        mbar_wait(&mbar[st], parity);
+        const ScatterItem d = desc[st];
+        const uint2* tile = raw + st * kScatterStageTuples + d.skip;
+        const uint32_t cnt = d.cnt;
+        __syncthreads();  // whist zeroed
         uint2 t[PER];
         uint32_t rank[PER];
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
-                t[j] = in[src0 + idx];
+                t[j] = tile[idx];
                 uint32_t pid = t[j].x & pmask;
                 uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
                 rank[j] = atomicAdd(&whist[wid][bin], 1u);
             }
         }
-        __syncthreads();
-        // per bin: turn per-warp counts into per-warp exclusive offsets, then scan the bin totals
+        __syncthreads();  // (A) every thread holds its tuples in registers: the stage can be refilled
+        if (threadIdx.x == 0) {
+            uint64_t nxt = item + (uint64_t)kScatterStages * gridDim.x;
+            if (nxt < nitems) issue(nxt, st);
+        }
+        // per bin: per-warp counts -> per-warp exclusive offsets; claim the bin's output range
         uint32_t tot = 0;
         if (threadIdx.x < nbins) {
+#pragma unroll
             for (int w = 0; w < NW; w++) {
                 uint32_t c = whist[w][threadIdx.x];
                 whist[w][threadIdx.x] = tot;
                 tot += c;
             }
-            binstart[threadIdx.x] = tot;  // inclusive-scan input
-            gclaim[threadIdx.x] = tot ? atomicAdd(&cursor[cbase + threadIdx.x], tot) : 0u;
+            binstart[threadIdx.x] = tot;
+            gclaim[threadIdx.x] = tot ? atomicAdd(&cursor[d.cbase + threadIdx.x], tot) : 0u;
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // exclusive scan over nbins (<=128) totals: 4 per lane
-            uint32_t v[4], s = 0;
+        __syncthreads();  // (B)
+        if (threadIdx.x < 32) {  // exclusive scan over nbins (<=128) totals: 4 per lane
+            uint32_t v[4], sum = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                uint32_t b = threadIdx.x * 4 + q;
-                v[q] = (b < nbins) ? binstart[b] : 0u;
-                s += v[q];
+                uint32_t bb = threadIdx.x * 4 + q;
+                v[q] = (bb < nbins) ? binstart[bb] : 0u;
+                sum += v[q];
             }
-            uint32_t inc = s;
+            uint32_t inc = sum;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((threadIdx.x & 31) >= d) inc += u;
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, inc, dd);
+                if ((int)threadIdx.x >= dd) inc += u;
             }
-            uint32_t run = inc - s;
+            uint32_t run = inc - sum;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                uint32_t b = threadIdx.x * 4 + q;
-                if (b < nbins) binstart[b] = run;
+                uint32_t bb = threadIdx.x * 4 + q;
+                if (bb < nbins) binstart[bb] = run;
                 run += v[q];
             }
         }
-        __syncthreads();
+        __syncthreads();  // (C)
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
@@ -429,14 +509,15 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __rest
                 sorted[binstart[bin] + whist[wid][bin] + rank[j]] = t[j];
             }
         }
-        __syncthreads();
+        __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
             uint2 tt = sorted[i];
             uint32_t pid = tt.x & pmask;
             uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
             out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = tt;
         }
-        __syncthreads();
+        // next iteration: whist is rewritten before (A'), binstart/gclaim after (A'), sorted after (C'): no
+        // thread can pass (A') before every thread has finished this write-out loop
     }
 }
 
@@ -495,7 +576,7 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
                                                       const uint2* __restrict__ Sp, const uint32_t* __restrict__ s_off,
                                                       const uint32_t* __restrict__ work_off, uint32_t P, uint32_t bits,
                                                       uint32_t* __restrict__ item_counter, JoinAccum* __restrict__ acc_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* tab = reinterpret_cast<uint2*>(smem_raw);                  // kTableCap tuples
     uint32_t* head = reinterpret_cast<uint32_t*>(tab + kTableCap);    // kTableCap heads (index+1, 0 = empty)
     uint16_t* next = reinterpret_cast<uint16_t*>(head + kTableCap);   // kTableCap links
@@ -503,6 +584,7 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
     __shared__ unsigned long long s_red[5][kJoinThreads / 32];
     unsigned long long matches = 0, cpair = 0, crpay = 0, cspay = 0, ckey = 0;
     const uint32_t total = work_off[P];
+    const uint64_t pol = policy_evict_first();
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(item_counter, 1u);
@@ -527,24 +609,47 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
             if (rb) __syncthreads();
             for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) head[i] = 0u;
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < cnt; i += kJoinThreads) {
-                uint2 t = Rp[(uint64_t)r0 + rb + i];
-                tab[i] = t;
-                uint32_t idx = (t.x >> bits) & nmask;
-                next[i] = (uint16_t)atomicExch(&head[idx], i + 1u);
+            constexpr int U = 4;  // independent 8-byte loads in flight per thread
+            const uint2* Rbase = Rp + (uint64_t)r0 + rb;
+            for (uint32_t i0 = threadIdx.x; i0 < cnt; i0 += U * kJoinThreads) {
+                uint2 t[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t i = i0 + u * kJoinThreads;
+                    if (i < cnt) t[u] = ld_stream_v2(Rbase + i, pol);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t i = i0 + u * kJoinThreads;
+                    if (i < cnt) {
+                        tab[i] = t[u];
+                        next[i] = (uint16_t)atomicExch(&head[(t[u].x >> bits) & nmask], i + 1u);
+                    }
+                }
             }
             __syncthreads();
-            for (uint32_t i = sbeg + threadIdx.x; i < send; i += kJoinThreads) {
-                uint2 s = Sp[i];
-                uint32_t idx = (s.x >> bits) & nmask;
-                for (uint32_t hit = head[idx]; hit; hit = next[hit - 1u]) {
-                    uint2 r = tab[hit - 1u];
-                    if (r.x == s.x) {
-                        matches++;
-                        cpair += mix64(r.y, s.y);
-                        crpay += r.y;
-                        cspay += s.y;
-                        ckey += s.x;
+            for (uint32_t i0 = sbeg + threadIdx.x; i0 < send; i0 += U * kJoinThreads) {
+                uint2 sv[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t i = i0 + u * kJoinThreads;
+                    if (i < send) sv[u] = ld_stream_v2(Sp + i, pol);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t i = i0 + u * kJoinThreads;
+                    if (i < send) {
+                        const uint2 s = sv[u];
+                        for (uint32_t hit = head[(s.x >> bits) & nmask]; hit; hit = next[hit - 1u]) {
+                            uint2 r = tab[hit - 1u];
+                            if (r.x == s.x) {
+                                matches++;
+                                cpair += mix64(r.y, s.y);
+                                crpay += r.y;
+                                cspay += s.y;
+                                ckey += s.x;
+                            }
+                        }
                     }
                 }
             }

@@ -36,6 +36,7 @@
 #include "tuple_buffer.h"
 #endif
 
+void * alloc_aligned(size_t size); /* generator.c:52, not declared in generator.h */
 extern int numalocalize; /* generator.c:46 */
 extern int nthreads;     /* generator.c:47 */
 
