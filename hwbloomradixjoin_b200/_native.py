@@ -50,7 +50,8 @@ EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_la
            "hwbrj_device_count", "hwbrj_check_args", "hwbrj_rel_upload", "hwbrj_rel_generate", "hwbrj_rel_download",
            "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_host_alloc", "hwbrj_host_free",
            "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_radix_partition",
-           "hwbrj_dist_unique_id", "hwbrj_dist_init", "hwbrj_dist_finalize", "hwbrj_join_device_dist"]
+           "hwbrj_set_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
+           "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe"]
 
 _lib = None
 
@@ -100,8 +101,19 @@ def load():
     L.hwbrj_bloom_probe.restype = C.c_int64
     L.hwbrj_bloom_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, argp, C.c_uint32, C.c_void_p]
     L.hwbrj_radix_partition.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
-    L.hwbrj_dist_unique_id.argtypes = [C.c_void_p]
-    L.hwbrj_dist_init.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
-    L.hwbrj_join_device_dist.argtypes = [C.c_void_p, C.c_void_p, argp, C.POINTER(StatsT)]
+    L.hwbrj_set_stream.argtypes = [C.c_void_p]
+    L.hwbrj_set_device.argtypes = [C.c_int]
+    L.hwbrj_rel_wrap.restype = C.c_void_p
+    L.hwbrj_rel_wrap.argtypes = [C.c_void_p, C.c_uint64]
+    L.hwbrj_rel_ptr.restype = C.c_void_p
+    L.hwbrj_rel_ptr.argtypes = [C.c_void_p]
+    L.hwbrj_rel_generate_shard.restype = C.c_void_p
+    L.hwbrj_rel_generate_shard.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64,
+                                           C.c_uint64]
+    L.hwbrj_owner_partition.argtypes = [C.c_void_p, C.c_int, argp, C.c_void_p, C.c_void_p]
+    L.hwbrj_filter_build.argtypes = [C.c_void_p, argp, C.c_void_p, C.c_int]
+    L.hwbrj_filter_or.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.hwbrj_filter_probe.restype = C.c_int64
+    L.hwbrj_filter_probe.argtypes = [C.c_void_p, C.c_void_p, argp, C.c_void_p]
     _lib = L
     return L

@@ -76,6 +76,7 @@ struct Ctx {
     int sms = 0;
     int clock_khz = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[8];
     uint32_t* d_crc = nullptr;
     DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, ctrl, rt1, rp, sc, st1, inR, inS, scratch;
@@ -101,7 +102,8 @@ static void init_ctx() {
     CK(cudaGetDeviceProperties(&pr, g.dev));
     g.sms = pr.multiProcessorCount;
     g.clock_khz = pr.clockRate;
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
     for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
     CrcTables T;
     crc_tables_fill(T);
@@ -118,6 +120,8 @@ static void init_ctx() {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_probe, k_probe_compact<7>, kProbeWarps * 32, 0));
     CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    CK(cudaFuncSetAttribute(k_scatter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    CK(cudaFuncSetAttribute(k_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter1, k_scatter<1>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter2, k_scatter<2>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join, kJoinThreads, kTableCap * (8 + 4 + 2)));
@@ -238,13 +242,18 @@ static const uint2* run_partition(const uint2* in, uint64_t n, const unsigned lo
     k_scan<<<1, 1024, 0, g.stream>>>(hist, P, (uint32_t)b2, off, g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(),
                                      g.tiles.as<uint32_t>());
     launches++;
-    k_scatter<1><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off,
-                                                        g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pmask,
-                                                        (uint32_t)b2, 1u << b1);
+    BinFn fn;
+    memset(&fn, 0, sizeof(fn));
+    fn.pmask = pmask;
+    fn.b2 = (uint32_t)b2;
+    fn.submask = (1u << b2) - 1u;
+    k_scatter<1><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(
+        in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), fn,
+        g.d_crc, 1u << b1);
     launches++;
     if (b2 == 0) return t1;
-    k_scatter<2><<<g.sms * g.occ_scatter2, kScatterThreads, kScatterSmem, g.stream>>>(t1, t2, nullptr, n, off, g.tiles.as<uint32_t>(),
-                                                        g.cur2.as<uint32_t>(), pmask, (uint32_t)b2, 1u << b2);
+    k_scatter<2><<<g.sms * g.occ_scatter2, kScatterThreads, kScatterSmem, g.stream>>>(
+        t1, t2, nullptr, n, off, g.tiles.as<uint32_t>(), g.cur2.as<uint32_t>(), fn, g.d_crc, 1u << b2);
     launches++;
     return t2;
 }
@@ -485,6 +494,7 @@ int hwbrj_check_args(const bloom_filter_args_t* args) { return args ? check_args
 struct hwbrj_rel {
     uint2* d;
     uint64_t n;
+    bool owned;
 };
 
 hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
@@ -492,25 +502,35 @@ hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
     init_ctx();
     hwbrj_rel_t* r = new hwbrj_rel;
     r->n = n;
+    r->owned = true;
     CK(cudaMalloc(&r->d, std::max<uint64_t>(n, 2) * 8 + 64));
     if (n) CK(cudaMemcpy(r->d, tuples, n * 8, cudaMemcpyHostToDevice));
     return r;
 }
 
 hwbrj_rel_t* hwbrj_rel_generate(int kind, uint64_t n, uint64_t r, double q, uint64_t seed) {
+    return hwbrj_rel_generate_shard(kind, n, r, q, seed, 0, n);
+}
+
+hwbrj_rel_t* hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double q, uint64_t seed, uint64_t begin,
+                                      uint64_t count) {
     std::lock_guard<std::mutex> lock(g.mu);
     init_ctx();
+    if (begin > n) begin = n;
+    if (count > n - begin) count = n - begin;
     hwbrj_rel_t* rel = new hwbrj_rel;
-    rel->n = n;
-    CK(cudaMalloc(&rel->d, std::max<uint64_t>(n, 2) * 8 + 64));
-    if (n) {
+    rel->n = count;
+    rel->owned = true;
+    CK(cudaMalloc(&rel->d, std::max<uint64_t>(count, 2) * 8 + 64));
+    if (count) {
         // generator.c:344: ntuples_above = num_tuples * (1 - selectivity)
         uint64_t na = kind == 1 ? (uint64_t)((double)n * (1.0 - q)) : 0;
         uint64_t nb = n - na;
         int bitsn = 1;
         while ((1ull << bitsn) < n) bitsn++;
         uint32_t half = (uint32_t)((bitsn + 1) / 2);
-        k_generate<<<g.sms * 8, 256, 0, g.stream>>>(rel->d, n, kind, r ? r : 1, nb, half, seed * 0x9e3779b97f4a7c15ULL + 12345);
+        k_generate<<<g.sms * 8, 256, 0, g.stream>>>(rel->d, n, kind, r ? r : 1, nb, half, seed * 0x9e3779b97f4a7c15ULL + 12345,
+                                                    begin, count);
         CK(cudaStreamSynchronize(g.stream));
         CK(cudaGetLastError());
     }
@@ -525,8 +545,35 @@ int hwbrj_rel_download(const hwbrj_rel_t* rel, tuple_t* out) {
 uint64_t hwbrj_rel_size(const hwbrj_rel_t* rel) { return rel ? rel->n : 0; }
 void hwbrj_rel_free(hwbrj_rel_t* rel) {
     if (!rel) return;
-    cudaFree(rel->d);
+    if (rel->owned) cudaFree(rel->d);
     delete rel;
+}
+hwbrj_rel_t* hwbrj_rel_wrap(void* device_tuples, uint64_t n) {
+    hwbrj_rel_t* r = new hwbrj_rel;
+    r->d = reinterpret_cast<uint2*>(device_tuples);
+    r->n = n;
+    r->owned = false;
+    return r;
+}
+void* hwbrj_rel_ptr(const hwbrj_rel_t* rel) { return rel ? rel->d : nullptr; }
+void hwbrj_set_stream(void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    g.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+}
+int hwbrj_set_device(int device) {
+    // must precede the first library call of the process (one process per GPU); buffers live on that device
+    if (g.inited && g.dev != device) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return -2;
+    }
+    return 0;
+}
+int hwbrj_sync(void) {
+    init_ctx();
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
 }
 
 int hwbrj_join_device(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, hwbrj_stats_t* out) {
@@ -652,10 +699,123 @@ int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out,
 
 }  // extern "C"
 
-// ---- multi-GPU (placeholder until the sharded pipeline lands) ----------------------------------------------------
-extern "C" {
-int hwbrj_dist_unique_id(void*) { return -1; }
-int hwbrj_dist_init(int, int, const void*, int) { return -1; }
-int hwbrj_dist_finalize(void) { return 0; }
-int hwbrj_join_device_dist(const hwbrj_rel_t*, const hwbrj_rel_t*, const bloom_filter_args_t*, hwbrj_stats_t*) { return -1; }
+// ---- multi-GPU building blocks: the host (hwbloomradixjoin_b200/dist.py, one process per GPU)
+// orchestrates these between torch.distributed collectives; all of them take raw device pointers and run on the
+// stream given to hwbrj_set_stream() ------------------------------------------------------------------------------
+namespace hwbrj {
+static BinFn owner_fn(int world, const bloom_filter_args_t* slice_args, int& mode) {
+    BinFn fn;
+    memset(&fn, 0, sizeof(fn));
+    const int gbits = ilog2_u64((uint64_t)world);
+    fn.seed = 42u;
+    if (slice_args && slice_args->variant == BLOCKED) {
+        mode = 4;  // owner = top bits of the block index (all k bits of a key live in that block)
+        uint64_t nblocks = slice_args->m / slice_args->B;
+        fn.size_mask = (uint32_t)(nblocks - 1);
+        fn.oshift = (uint32_t)std::max(0, ilog2_u64(nblocks) - gbits);
+    } else if (slice_args) {
+        mode = 3;  // owner = top bits of the first bit address crapwow & (m-1)
+        fn.size_mask = (uint32_t)(slice_args->m - 1);
+        fn.oshift = (uint32_t)std::max(0, ilog2_u64(slice_args->m) - gbits);
+    } else {
+        mode = 3;  // no sliceable filter: owner = top bits of crapwow(42,key)
+        fn.size_mask = 0xFFFFFFFFu;
+        fn.oshift = (uint32_t)(32 - gbits);
+    }
+    return fn;
 }
+}  // namespace hwbrj
+
+extern "C" {
+
+int hwbrj_owner_partition(const hwbrj_rel_t* in, int world, const bloom_filter_args_t* slice_args, void* d_out,
+                          uint64_t* counts_out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!in || world < 1 || world > 128 || (world & (world - 1)) || in->n >= (1ull << 32)) return -1;
+    if (slice_args && check_args_impl(slice_args, true)) return -1;
+    if (slice_args && slice_args->variant == BASIC && slice_args->k > 1) slice_args = nullptr;  // not sliceable
+    if (slice_args) {
+        uint64_t units = slice_args->variant == BLOCKED ? slice_args->m / slice_args->B : slice_args->m;
+        if (units < (uint64_t)world) return -1;
+    }
+    ensure_workspace(1, 1, nullptr);
+    int mode = 3;
+    BinFn fn = owner_fn(world, slice_args, mode);
+    const uint32_t nb = (uint32_t)world;
+    CK(cudaMemsetAsync(g.histR.p, 0, nb * 4, g.stream));
+    if (mode == 4)
+        k_owner_hist<4><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, nullptr, fn, g.d_crc, nb, g.histR.as<uint32_t>());
+    else
+        k_owner_hist<3><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, nullptr, fn, g.d_crc, nb, g.histR.as<uint32_t>());
+    k_scan<<<1, 1024, 0, g.stream>>>(g.histR.as<uint32_t>(), nb, 0u, g.offR.as<uint32_t>(), g.cur1.as<uint32_t>(),
+                                     g.cur2.as<uint32_t>(), g.tiles.as<uint32_t>());
+    if (mode == 4)
+        k_scatter<4><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(
+            in->d, reinterpret_cast<uint2*>(d_out), nullptr, in->n, g.offR.as<uint32_t>(), g.tiles.as<uint32_t>(),
+            g.cur1.as<uint32_t>(), fn, g.d_crc, nb);
+    else
+        k_scatter<3><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(
+            in->d, reinterpret_cast<uint2*>(d_out), nullptr, in->n, g.offR.as<uint32_t>(), g.tiles.as<uint32_t>(),
+            g.cur1.as<uint32_t>(), fn, g.d_crc, nb);
+    std::vector<uint32_t> off(nb + 1);
+    CK(cudaMemcpyAsync(off.data(), g.offR.p, (nb + 1) * 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    for (uint32_t i = 0; i < nb; i++) counts_out[i] = off[i + 1] - off[i];
+    return 0;
+}
+
+int hwbrj_filter_build(const hwbrj_rel_t* R, const bloom_filter_args_t* args, void* d_filter, int zero_first) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!R || !args || !d_filter || check_args_impl(args, true)) return -1;
+    g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
+    if (zero_first) CK(cudaMemsetAsync(d_filter, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
+    CK(cudaMemsetAsync(g.histR.p, 0, 4, g.stream));
+    BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(d_filter));
+    int nranges = pick_ranges(args);
+    bp.nranges = (uint32_t)nranges;
+    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + 1024) * 4, g.stream>>>(R->d, R->n, nullptr, bp, g.d_crc,
+                                                                          g.histR.as<uint32_t>(), 0u);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hwbrj_filter_or(void* d_dst, const void* d_src, uint64_t nbytes) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (nbytes % 16) return -1;
+    k_filter_or<<<g.sms * 8, 256, 0, g.stream>>>(reinterpret_cast<uint4*>(d_dst), reinterpret_cast<const uint4*>(d_src),
+                                                 nbytes / 16);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int64_t hwbrj_filter_probe(const void* d_filter, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!S || !args || !d_filter || !d_out || check_args_impl(args, true)) return -1;
+    g.ctrl.ensure(sizeof(Control));
+    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
+    Control* ctrl = g.ctrl.as<Control>();
+    BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(const_cast<void*>(d_filter)));
+    int nranges = pick_ranges(args);
+    bp.nranges = (uint32_t)nranges;
+    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        launch_probe(S->d, S->n, bp, reinterpret_cast<uint2*>(d_out), &ctrl->survivors);
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    return (int64_t)cnt;
+}
+
+}  // extern "C"

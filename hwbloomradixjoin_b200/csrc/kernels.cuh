@@ -356,6 +356,55 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist
     for (uint32_t j = threadIdx.x; j <= P1; j += blockDim.x) tile_off[j] = s_tiles[j];
 }
 
+// ---- destination-bin functions of the scatter kernel -----------------------------------------------------------------
+// MODE 1: radix level 1 (pid >> b2)      MODE 2: radix level 2 (pid & (2^b2-1))
+// MODE 3: owner GPU by hash slice, BASIC filter / plain join: (crapwow(seed,key) & size_mask) >> oshift
+// MODE 4: owner GPU by hash slice, BLOCKED filter: (crc32c(seed,key) & nblocks_mask) >> oshift
+struct BinFn {
+    uint32_t pmask, b2, submask;            // radix modes
+    uint32_t seed, size_mask, oshift;       // owner modes
+};
+template <int MODE>
+__device__ __forceinline__ uint32_t bin_of(const BinFn& f, const uint32_t* crc_tab, uint32_t key) {
+    if (MODE == 1) return (key & f.pmask) >> f.b2;
+    if (MODE == 2) return key & f.submask;
+    if (MODE == 3) return (hash_crapwow(f.seed, key) & f.size_mask) >> f.oshift;
+    return (crc32c_tab(crc_tab, f.seed, key) & f.size_mask) >> f.oshift;
+}
+
+// histogram of owner bins (<= 128): per-warp shared counters, flushed with global atomics
+template <int MODE>
+__global__ void __launch_bounds__(256) k_owner_hist(const uint2* __restrict__ in, uint64_t n_static,
+                                                    const unsigned long long* __restrict__ n_ptr, BinFn f,
+                                                    const uint32_t* __restrict__ g_crc, uint32_t nbins,
+                                                    uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t wh[8][1 << kMaxLevelBits];
+    __shared__ uint32_t crc_tab[MODE == 4 ? 1024 : 1];
+    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
+    for (uint32_t i = threadIdx.x; i < 8 * nbins; i += blockDim.x) wh[i / nbins][i % nbins] = 0u;
+    if (MODE == 4) load_crc_tab(crc_tab, g_crc);
+    __syncthreads();
+    const uint32_t wid = threadIdx.x >> 5;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&wh[wid][bin_of<MODE>(f, crc_tab, in[i].x)], 1u);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
+        uint32_t c = 0;
+        for (int w = 0; w < 8; w++) c += wh[w][b];
+        if (c) atomicAdd(&ghist[b], c);
+    }
+}
+
+// bitwise OR of a partial filter into the destination (multi-GPU general path: NCCL has no OR reduction)
+__global__ void k_filter_or(uint4* __restrict__ dst, const uint4* __restrict__ src, uint64_t n16) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 a = dst[i], b = src[i];
+        dst[i] = make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+    }
+}
+
 // ---- K4: radix scatter with shared-memory staging ---------------------------------------------------------------
 // replaces the scatter loop (:842-849) and pass-2 radix_cluster (:574-608).
 // Persistent CTAs; every CTA walks its tiles of kScatterTile tuples through a kScatterStages-deep ring of TMA
@@ -373,12 +422,12 @@ struct ScatterItem {
     uint32_t bytes;    // bulk-load size
 };
 
-template <int LEVEL>
+template <int MODE>
 __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ fine_off,
                                                     const uint32_t* __restrict__ tile_off, uint32_t P1, uint32_t b2) {
     ScatterItem it;
     uint64_t src0;
-    if (LEVEL == 1) {
+    if (MODE != 2) {
         src0 = item * kScatterTile;
         it.cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
         it.cbase = 0u;
@@ -399,13 +448,13 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
     return it;
 }
 
-template <int LEVEL>
+template <int MODE>
 __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
                                                             const uint64_t* __restrict__ n_ptr, uint64_t n_static,
                                                             const uint32_t* __restrict__ fine_off,
                                                             const uint32_t* __restrict__ tile_off,
-                                                            uint32_t* __restrict__ cursor, uint32_t pmask, uint32_t b2,
-                                                            uint32_t nbins) {
+                                                            uint32_t* __restrict__ cursor, BinFn fn,
+                                                            const uint32_t* __restrict__ g_crc, uint32_t nbins) {
     constexpr int NW = kScatterThreads / 32;
     constexpr int PER = kScatterTile / kScatterThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -416,18 +465,21 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __rest
     __shared__ uint32_t gclaim[1 << kMaxLevelBits];
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
+    __shared__ uint8_t sorted_bin[kScatterTile];
+    __shared__ uint32_t crc_tab[MODE == 4 ? 1024 : 1];
     const uint32_t wid = threadIdx.x >> 5;
     const uint64_t n = n_ptr ? *n_ptr : n_static;
-    const uint32_t P1 = (pmask + 1u) >> b2;
-    const uint64_t nitems = (LEVEL == 1) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
-    const uint32_t submask = (1u << b2) - 1u;
+    const uint32_t b2 = fn.b2;
+    const uint32_t P1 = (fn.pmask + 1u) >> b2;
+    const uint64_t nitems = (MODE != 2) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
+    if (MODE == 4) load_crc_tab(crc_tab, g_crc);
     if (threadIdx.x == 0) {
         for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
         mbar_fence_init();
     }
     __syncthreads();
     auto issue = [&](uint64_t item, int st) {  // thread 0 only
-        ScatterItem it = scatter_item<LEVEL>(item, n, fine_off, tile_off, P1, b2);
+        ScatterItem it = scatter_item<MODE>(item, n, fine_off, tile_off, P1, b2);
         desc[st] = it;
         mbar_arrive_expect_tx(&mbar[st], it.bytes);
         bulk_g2s(raw + st * kScatterStageTuples, in + it.src_al, it.bytes, &mbar[st]);
@@ -448,15 +500,14 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __rest
         const uint32_t cnt = d.cnt;
         __syncthreads();  // whist zeroed
         uint2 t[PER];
-        uint32_t rank[PER];
+        uint32_t rank[PER];  // bin in the high 8 bits, rank within (warp, bin) in the low 24
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
                 t[j] = tile[idx];
-                uint32_t pid = t[j].x & pmask;
-                uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
-                rank[j] = atomicAdd(&whist[wid][bin], 1u);
+                uint32_t bin = bin_of<MODE>(fn, crc_tab, t[j].x);
+                rank[j] = (bin << 24) | atomicAdd(&whist[wid][bin], 1u);
             }
         }
         __syncthreads();  // (A) every thread holds its tuples in registers: the stage can be refilled
@@ -504,17 +555,16 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __rest
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
-                uint32_t pid = t[j].x & pmask;
-                uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
-                sorted[binstart[bin] + whist[wid][bin] + rank[j]] = t[j];
+                uint32_t bin = rank[j] >> 24;
+                uint32_t pos = binstart[bin] + whist[wid][bin] + (rank[j] & 0xFFFFFFu);
+                sorted[pos] = t[j];
+                sorted_bin[pos] = (uint8_t)bin;
             }
         }
         __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
-            uint2 tt = sorted[i];
-            uint32_t pid = tt.x & pmask;
-            uint32_t bin = (LEVEL == 1) ? (pid >> b2) : (pid & submask);
-            out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = tt;
+            uint32_t bin = sorted_bin[i];
+            out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = sorted[i];
         }
         // next iteration: whist is rewritten before (A'), binstart/gclaim after (A'), sorted after (C'): no
         // thread can pass (A') before every thread has finished this write-out loop
@@ -694,10 +744,12 @@ __device__ __forceinline__ uint64_t feistel_perm(uint64_t x, uint64_t n, uint32_
 
 // kind 0: R = permutation of 1..n, payload = position (main.c:430-431)
 // kind 1: S = nb keys ((e mod r)+1) and na keys r+1+e', payload = position (main.c:464-465)
+// The kernel fills positions [begin, begin+count) of the global relation of n tuples (a shard).
 __global__ void k_generate(uint2* __restrict__ out, uint64_t n, int kind, uint64_t r, uint64_t nb, uint32_t half_bits,
-                           uint64_t seed) {
+                           uint64_t seed, uint64_t begin, uint64_t count) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; li < count; li += stride) {
+        const uint64_t i = begin + li;
         uint64_t e = feistel_perm(i, n, half_bits, seed);
         uint32_t key;
         if (kind == 0) key = (uint32_t)(e + 1ull);
@@ -706,7 +758,7 @@ __global__ void k_generate(uint2* __restrict__ out, uint64_t n, int kind, uint64
             uint64_t span = 2147483647ull - r;  // keys wrap back to r+1 after INT_MAX (generator.c:191-193)
             key = (uint32_t)(r + 1ull + (e - nb) % (span ? span : 1ull));
         }
-        out[i] = make_uint2(key, (uint32_t)i);
+        out[li] = make_uint2(key, (uint32_t)i);
     }
 }
 

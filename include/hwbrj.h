@@ -182,15 +182,30 @@ int64_t hwbrj_bloom_probe(const unsigned char * bitmap, const tuple_t * S, uint6
  * partition boundaries (parallel_radix_join_bloom.c:574-608,759-852 equivalent) */
 int hwbrj_radix_partition(const tuple_t * in, uint64_t n, int bits, tuple_t * out, uint64_t * offsets);
 
-/* ---- multi-GPU (one process per GPU, NCCL bootstrap through the host's own channel) --------- */
-#define HWBRJ_NCCL_ID_BYTES 128
-int hwbrj_dist_unique_id(void * id_out /* HWBRJ_NCCL_ID_BYTES */);
-int hwbrj_dist_init(int rank, int world, const void * id, int local_device);
-int hwbrj_dist_finalize(void);
-/* collective join: every rank passes its local shard of R and S (device-resident); the scalars in
- * `out` are the all-reduced global results, identical on every rank. */
-int hwbrj_join_device_dist(const hwbrj_rel_t * Rshard, const hwbrj_rel_t * Sshard,
-                           const bloom_filter_args_t * args, hwbrj_stats_t * out);
+/* ---- multi-GPU building blocks ------------------------------------------------------------
+ * One process per GPU; the host side (hwbloomradixjoin_b200/dist.py) runs these between torch.distributed / NCCL
+ * collectives. All take device pointers and run on the stream given to hwbrj_set_stream(). */
+void hwbrj_set_stream(void * cuda_stream); /* NULL: the library's own stream */
+int  hwbrj_sync(void);
+int  hwbrj_set_device(int device);           /* before the first call: one process per GPU */
+hwbrj_rel_t * hwbrj_rel_wrap(void * device_tuples, uint64_t n); /* non-owning view of device memory */
+void *        hwbrj_rel_ptr(const hwbrj_rel_t * rel);
+/* positions [begin, begin+count) of the global generated relation (a rank's contiguous input chunk, the GPU
+ * analogue of the per-thread chunks of parallel_radix_join_bloom.c:1646-1672) */
+hwbrj_rel_t * hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double q, uint64_t seed, uint64_t begin,
+                                       uint64_t count);
+/* group the tuples by owner GPU into d_out (n tuples) and return the per-owner counts (host array of `world`).
+ * Owner = the GPU holding the filter slice of the key's first bit (slice_args BASIC k<=1 or BLOCKED), else the
+ * top bits of crapwow(42,key); equal keys always share an owner, so owners join independently. */
+int hwbrj_owner_partition(const hwbrj_rel_t * in, int world, const bloom_filter_args_t * slice_args, void * d_out,
+                          uint64_t * counts_out);
+/* insert R's keys into the full-size filter at d_filter (m/8 bytes, device) */
+int hwbrj_filter_build(const hwbrj_rel_t * R, const bloom_filter_args_t * args, void * d_filter, int zero_first);
+/* dst |= src over nbytes (multiple of 16): combines partial filters (NCCL has no bitwise-OR reduction) */
+int hwbrj_filter_or(void * d_dst, const void * d_src, uint64_t nbytes);
+/* probe S against the device filter; survivors (any order) go to d_out (capacity |S| tuples); returns the count */
+int64_t hwbrj_filter_probe(const void * d_filter, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
+                           void * d_out);
 
 #ifdef __cplusplus
 }

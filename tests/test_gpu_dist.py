@@ -1,0 +1,58 @@
+"""2-GPU test of the sharded join (-m gpu; skipped on a single-GPU box): torchrun with two ranks over NCCL must
+reproduce the single-GPU scalars. One rank per GPU -- ranks are never stacked on one device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import json, os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HWBRJ_ROOT"])
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+from hwbloomradixjoin_b200 import BloomFilterArgs
+from hwbloomradixjoin_b200.dist import CudaOps, dist_join
+ops = CudaOps(dev)
+r, s, q = 2_000_000, 16_000_000, 0.01
+per_r, per_s = r // world, s // world
+R = ops.generate_shard(0, r, r, 1.0, 1, rank * per_r, r - rank * per_r if rank == world - 1 else per_r)
+S = ops.generate_shard(1, s, r, q, 2, rank * per_s, s - rank * per_s if rank == world - 1 else per_s)
+out = []
+for case in [(0, 1 << 24, 1, 512), (0, 1 << 24, 3, 512), (1, 1 << 24, 4, 256), None]:
+    res = dist_join(ops, R, S, BloomFilterArgs(*case) if case else None)
+    out.append({k: res[k] for k in ("matches", "filtered", "checksum_pair", "checksum_key", "sliced_filter", "tuples_over_nvlink_s")})
+if rank == 0:
+    print("RESULT " + json.dumps(out))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path):
+    if Hgpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one rank per GPU)")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, HWBRJ_ROOT=ROOT)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")][0]
+    got = json.loads(line[7:])
+    r, s, q = 2_000_000, 16_000_000, 0.01
+    dR = Hgpu.DeviceRelation.generate(0, r, r, 1.0, 1)
+    dS = Hgpu.DeviceRelation.generate(1, s, r, q, 2)
+    for case, g in zip([(0, 1 << 24, 1, 512), (0, 1 << 24, 3, 512), (1, 1 << 24, 4, 256), None], got):
+        one = Hgpu.join_device(dR, dS, Hgpu.BloomFilterArgs(*case) if case else None)
+        assert (g["matches"], g["filtered"], g["checksum_pair"], g["checksum_key"]) == \
+               (one.totalresults, one.filtered, one.checksum_pair, one.checksum_key), case
+        if case:
+            assert g["tuples_over_nvlink_s"] <= one.filtered
