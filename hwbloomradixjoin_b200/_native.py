@@ -50,7 +50,7 @@ EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_la
            "hwbrj_device_count", "hwbrj_check_args", "hwbrj_rel_upload", "hwbrj_rel_generate", "hwbrj_rel_download",
            "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_host_alloc", "hwbrj_host_free",
            "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_radix_partition",
-           "hwbrj_set_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
+           "hwbrj_set_stream", "hwbrj_reset_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
            "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe"]
 
 _lib = None

@@ -559,7 +559,12 @@ void* hwbrj_rel_ptr(const hwbrj_rel_t* rel) { return rel ? rel->d : nullptr; }
 void hwbrj_set_stream(void* cuda_stream) {
     std::lock_guard<std::mutex> lock(g.mu);
     init_ctx();
-    g.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    g.stream = reinterpret_cast<cudaStream_t>(cuda_stream);  // 0 is a valid handle: the legacy default stream
+}
+void hwbrj_reset_stream(void) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    g.stream = g.own_stream;
 }
 int hwbrj_set_device(int device) {
     // must precede the first library call of the process (one process per GPU); buffers live on that device

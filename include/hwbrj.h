@@ -185,7 +185,8 @@ int hwbrj_radix_partition(const tuple_t * in, uint64_t n, int bits, tuple_t * ou
 /* ---- multi-GPU building blocks ------------------------------------------------------------
  * One process per GPU; the host side (hwbloomradixjoin_b200/dist.py) runs these between torch.distributed / NCCL
  * collectives. All take device pointers and run on the stream given to hwbrj_set_stream(). */
-void hwbrj_set_stream(void * cuda_stream); /* NULL: the library's own stream */
+void hwbrj_set_stream(void * cuda_stream); /* run on the caller's stream (0 = the legacy default stream) */
+void hwbrj_reset_stream(void);             /* back to the library's own stream */
 int  hwbrj_sync(void);
 int  hwbrj_set_device(int device);           /* before the first call: one process per GPU */
 hwbrj_rel_t * hwbrj_rel_wrap(void * device_tuples, uint64_t n); /* non-owning view of device memory */
