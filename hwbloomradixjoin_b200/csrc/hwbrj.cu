@@ -64,7 +64,7 @@ struct DevBuf {
 // small control block living in one allocation (zeroed with one memset per join)
 struct Control {
     unsigned long long survivors;  // K2 output cursor == filtered
-    unsigned long long n_s_static; // unused slot (keeps 16B alignment)
+    unsigned long long defer[7];   // sizes of the deferred inputs of range passes 1..7
     JoinAccum acc;
     uint32_t item_counter;
     uint32_t pad[3];
@@ -85,6 +85,8 @@ struct Ctx {
     int radix_bits_override = 0;
     int range_passes_override = 0;
     int probe_ctas_per_sm = 0;  // 0 = occupancy API
+    bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
+    DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
     int occ_probe = 1, occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
     std::mutex mu;
 };
@@ -109,7 +111,7 @@ static void init_ctx() {
     crc_tables_fill(T);
     CK(cudaMalloc(&g.d_crc, sizeof(T)));
     CK(cudaMemcpy(g.d_crc, &T, sizeof(T), cudaMemcpyHostToDevice));
-    const int hist_smem = ((1 << kMaxRadixBits) + 1024) * 4;
+    const int hist_smem = ((1 << kMaxRadixBits) + kCrcSmemWords) * 4;
     CK(cudaFuncSetAttribute(k_build_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     CK(cudaFuncSetAttribute(k_join, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
@@ -117,7 +119,7 @@ static void init_ctx() {
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_probe, k_probe_compact<7>, kProbeWarps * 32, 0));
+    if (const char* s = getenv("HWBRJ_DEFER")) g.defer_ranges = atoi(s) != 0;
     CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
@@ -125,7 +127,6 @@ static void init_ctx() {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter1, k_scatter<1>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter2, k_scatter<2>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join, kJoinThreads, kTableCap * (8 + 4 + 2)));
-    g.occ_probe = std::max(g.occ_probe, 1);
     g.occ_scatter1 = std::max(g.occ_scatter1, 1);
     g.occ_scatter2 = std::max(g.occ_scatter2, 1);
     g.occ_join = std::max(g.occ_join, 1);
@@ -206,26 +207,62 @@ static int pick_bits(uint64_t nR) {
 }
 
 
-// K2 launch with compile-time specialisation on (blocked, k == 1, ranged)
-static void launch_probe(const uint2* dS, uint64_t nS, const BloomParams& bp, uint2* out, unsigned long long* cursor) {
-    const int mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0) | (bp.nranges > 1u ? 4 : 0);
-    static int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define HWBRJ_PROBE_CASE(M)                                                                                        \
-    case M: {                                                                                                      \
-        if (!occ[M]) {                                                                                             \
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[M], k_probe_compact<M>, kProbeWarps * 32, 0));   \
-            occ[M] = std::max(occ[M], 1);                                                                          \
-        }                                                                                                          \
-        /* measured on B200: 4 CTAs/SM beats the occupancy maximum (less L2 thrash of the filter range) */ \
-        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(occ[M], 4));                             \
-        k_probe_compact<M><<<grid, kProbeWarps * 32, 0, g.stream>>>(dS, nS, bp, g.d_crc, out, cursor);            \
-        break;                                                                                                     \
+// K2 launch with compile-time specialisation on (blocked, k == 1, ranged, defer)
+static void launch_probe_mode(int mode, const uint2* in, uint64_t n, const unsigned long long* n_ptr, const BloomParams& bp,
+                              uint2* out, unsigned long long* cursor, uint2* defer_out, unsigned long long* defer_cursor) {
+    static int occ[16] = {0};
+#define HWBRJ_PROBE_CASE(M)                                                                                         \
+    case M: {                                                                                                       \
+        const int smem = kProbeWarps * kProbeSmemPerWarp(M);                                                        \
+        if (!occ[M]) {                                                                                              \
+            CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[M], k_probe_compact<M>, kProbeWarps * 32, smem)); \
+            occ[M] = std::max(occ[M], 1);                                                                           \
+        }                                                                                                           \
+        /* measured on B200: 4 CTAs/SM beats the occupancy maximum (less L2 thrash of the filter range) */          \
+        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(occ[M], 4));                 \
+        k_probe_compact<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor,     \
+                                                                       defer_out, defer_cursor);                    \
+        break;                                                                                                      \
     }
     switch (mode) {
         HWBRJ_PROBE_CASE(0) HWBRJ_PROBE_CASE(1) HWBRJ_PROBE_CASE(2) HWBRJ_PROBE_CASE(3)
         HWBRJ_PROBE_CASE(4) HWBRJ_PROBE_CASE(5) HWBRJ_PROBE_CASE(6) HWBRJ_PROBE_CASE(7)
+        HWBRJ_PROBE_CASE(12) HWBRJ_PROBE_CASE(13) HWBRJ_PROBE_CASE(14) HWBRJ_PROBE_CASE(15)
+        default: die("bad probe mode %d", mode);
     }
 #undef HWBRJ_PROBE_CASE
+}
+
+// All range passes of the S-side probe. With deferral (default) pass i reads what pass i-1 deferred, so S itself is
+// read once; buffers d0/d1 (|S| tuples each) ping-pong. Returns the number of kernel launches.
+static int run_probe(const uint2* dS, uint64_t nS, BloomParams bp, int nranges, uint2* out, Control* ctrl, uint2* d0,
+                     uint2* d1) {
+    const int base_mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0);
+    bp.nranges = (uint32_t)nranges;
+    if (nranges == 1) {
+        launch_probe_mode(base_mode, dS, nS, nullptr, bp, out, &ctrl->survivors, nullptr, nullptr);
+        return 1;
+    }
+    const bool defer = g.defer_ranges && d0 && (nranges == 2 || d1);
+    const uint2* in = dS;
+    const unsigned long long* n_ptr = nullptr;
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        if (!defer) {
+            launch_probe_mode(base_mode | 4, dS, nS, nullptr, bp, out, &ctrl->survivors, nullptr, nullptr);
+        } else if (r + 1 < nranges) {
+            uint2* dout = (r & 1) ? d1 : d0;
+            launch_probe_mode(base_mode | 4 | 8, in, nS, n_ptr, bp, out, &ctrl->survivors, dout, &ctrl->defer[r]);
+            in = dout;
+            n_ptr = &ctrl->defer[r];
+        } else {
+            BloomParams last = bp;  // everything left belongs to the last range: no range test needed
+            last.nranges = 1;
+            launch_probe_mode(base_mode, in, nS, n_ptr, last, out, &ctrl->survivors, nullptr, nullptr);
+        }
+    }
+    return nranges;
 }
 
 struct Partitioned {
@@ -301,7 +338,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
     int nranges = 1;
-    const int hist_smem = (int)((P + 1024) * 4);
+    const int hist_smem = (int)((P + kCrcSmemWords) * 4);
     const int grid_hist = g.sms * 2;
     if (args) {
         bp = make_bloom(args, 42u, g.filter.as<uint32_t>());  // seed 42: parallel_radix_join_bloom.c:1583,1823
@@ -324,11 +361,9 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     const uint2* Sin = dS;
     const unsigned long long* n_dev = nullptr;
     if (args) {
-        for (int r = 0; r < nranges; r++) {
-            bp.range_id = (uint32_t)r;
-            launch_probe(dS, nS, bp, g.sc.as<uint2>(), &ctrl->survivors);
-            launches++;
-        }
+        if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(nS, 1) * 8);
+        launches += run_probe(dS, nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
+                              nranges > 2 ? g.d1.as<uint2>() : nullptr);
         Sin = g.sc.as<uint2>();
         n_dev = &ctrl->survivors;
     }
@@ -636,7 +671,7 @@ int hwbrj_bloom_build(const tuple_t* R, uint64_t nR, const bloom_filter_args_t* 
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + 1024) * 4, g.stream>>>(g.inR.as<uint2>(), nR, nullptr, bp, g.d_crc,
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(g.inR.as<uint2>(), nR, nullptr, bp, g.d_crc,
                                                                           g.histR.as<uint32_t>(), 0u);
     }
     CK(cudaMemcpyAsync(bitmap_out, g.filter.p, args->m / 8, cudaMemcpyDeviceToHost, g.stream));
@@ -664,10 +699,10 @@ int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_
     int nranges = pick_ranges(args);
     bp.nranges = (uint32_t)nranges;
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    for (int r = 0; r < nranges; r++) {
-        bp.range_id = (uint32_t)r;
-        launch_probe(g.inS.as<uint2>(), nS, bp, g.sc.as<uint2>(), &ctrl->survivors);
-    }
+    g.st1.ensure(std::max<uint64_t>(nS, 1) * 8);
+    if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(nS, 1) * 8);
+    run_probe(g.inS.as<uint2>(), nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
+              nranges > 2 ? g.d1.as<uint2>() : nullptr);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -688,7 +723,7 @@ int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out,
     CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
-    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + 1024) * 4), g.stream>>>(g.inR.as<uint2>(), n, nullptr, bp, g.d_crc,
+    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + kCrcSmemWords) * 4), g.stream>>>(g.inR.as<uint2>(), n, nullptr, bp, g.d_crc,
                                                                             g.histR.as<uint32_t>(), P - 1u);
     int launches = 0;
     const uint2* res = run_partition(g.inR.as<uint2>(), n, nullptr, bits, b2, g.histR.as<uint32_t>(),
@@ -784,7 +819,7 @@ int hwbrj_filter_build(const hwbrj_rel_t* R, const bloom_filter_args_t* args, vo
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + 1024) * 4, g.stream>>>(R->d, R->n, nullptr, bp, g.d_crc,
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, nullptr, bp, g.d_crc,
                                                                           g.histR.as<uint32_t>(), 0u);
     }
     CK(cudaGetLastError());
@@ -812,10 +847,10 @@ int64_t hwbrj_filter_probe(const void* d_filter, const hwbrj_rel_t* S, const blo
     int nranges = pick_ranges(args);
     bp.nranges = (uint32_t)nranges;
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    for (int r = 0; r < nranges; r++) {
-        bp.range_id = (uint32_t)r;
-        launch_probe(S->d, S->n, bp, reinterpret_cast<uint2*>(d_out), &ctrl->survivors);
-    }
+    g.st1.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    run_probe(S->d, S->n, bp, nranges, reinterpret_cast<uint2*>(d_out), ctrl, g.st1.as<uint2>(),
+              nranges > 2 ? g.d1.as<uint2>() : nullptr);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));

@@ -14,11 +14,29 @@ namespace hwbrj {
 constexpr int kMaxLevelBits = 7;                     // radix bits per scatter pass
 constexpr int kMaxRadixBits = 2 * kMaxLevelBits;     // 2 passes
 constexpr int kTableCap = 8192;                      // R tuples per shared-memory hash table
-constexpr int kJoinThreads = 512;
+#ifndef HWBRJ_JOIN_THREADS
+#define HWBRJ_JOIN_THREADS 512
+#endif
+#ifndef HWBRJ_JOIN_UNROLL
+#define HWBRJ_JOIN_UNROLL 4
+#endif
+#ifndef HWBRJ_SCATTER_THREADS
+#define HWBRJ_SCATTER_THREADS 256
+#endif
+#ifndef HWBRJ_SCATTER_TILE
+#define HWBRJ_SCATTER_TILE 2048
+#endif
+#ifndef HWBRJ_SCATTER_STAGES
+#define HWBRJ_SCATTER_STAGES 2
+#endif
+#ifndef HWBRJ_SCATTER_MINBLOCKS
+#define HWBRJ_SCATTER_MINBLOCKS 1
+#endif
+constexpr int kJoinThreads = HWBRJ_JOIN_THREADS;
 constexpr int kSChunk = 32768;                       // S tuples per join work item
-constexpr int kScatterThreads = 256;
-constexpr int kScatterTile = 2048;                   // tuples per scatter tile
-constexpr int kScatterStages = 3;                    // TMA bulk-load ring depth
+constexpr int kScatterThreads = HWBRJ_SCATTER_THREADS;
+constexpr int kScatterTile = HWBRJ_SCATTER_TILE;     // tuples per scatter tile
+constexpr int kScatterStages = HWBRJ_SCATTER_STAGES; // TMA bulk-load ring depth
 constexpr int kScatterStageTuples = kScatterTile + 2; // +1 misaligned head, +1 rounding to 16 bytes
 constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTile) * 8;
 constexpr int kProbeV = 4;                           // 128-bit loads in flight per lane in K2
@@ -49,7 +67,9 @@ __device__ __forceinline__ uint64_t mix64(uint32_t rpay, uint32_t spay) {
     return z ^ (z >> 31);
 }
 
-// streaming 128-bit load: read-once data must not displace the filter in L2
+// streaming 128-bit load: read-once data must not displace the filter in L2. In the micro-benchmark ld.global.cs
+// + evict_last probes looked 6% better, in the real K2 it is 10% worse than this evict_first policy + plain __ldg
+// probes (5.9 vs 5.3 ms at C1), so this is what ships.
 __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p, uint64_t pol) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
@@ -138,7 +158,7 @@ __device__ __forceinline__ bool bloom_test_rest(const BloomParams& bp, uint32_t 
 }
 
 __device__ __forceinline__ void load_crc_tab(uint32_t* s_tab, const uint32_t* __restrict__ g_tab) {
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = g_tab[i];
+    for (int i = threadIdx.x; i < kCrcSmemWords; i += blockDim.x) s_tab[i] = g_tab[i];
 }
 
 // ---- K0: hash library entry ---------------------------------------------------------------------------------
@@ -152,7 +172,7 @@ __global__ void k_hash_many(int which, uint32_t seed, const int32_t* __restrict_
 // ---- K1 (+K3 histogram): Bloom insert fused with the radix histogram of R ------------------------------------
 // replaces the build branch of the histogram loop, parallel_radix_join_bloom.c:794-805 + add_generic
 // (bloom_filter.c:74-89). Also used without a filter (plain PRO histogram, parallel_radix_join.c:770-775).
-// dynamic smem: hist[pmask+1] then crc table[1024]
+// dynamic smem: hist[pmask+1] then crc table[kCrcSmemWords]
 template <bool BLOOM>
 __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ rel, uint64_t n_static,
                                                     const unsigned long long* __restrict__ n_ptr, BloomParams bp,
@@ -199,19 +219,58 @@ __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ r
 // together, and appends survivors to its private shared-memory ring; whenever the ring holds kWarpFlush
 // tuples the warp claims kWarpFlush slots of the output with ONE global atomic and writes them as whole
 // 128-byte lines (claims are multiples of kWarpFlush, so every flush but the last is line-aligned).
-constexpr int kWarpFlush = 256;              // tuples per flush (2 KB)
-constexpr int kWarpRing = 2 * kWarpFlush;    // ring capacity per warp (power of two)
 constexpr int kProbeWarps = 8;               // warps per CTA
-// MODE bit0: BLOCKED, bit1: single probe (k == 1), bit2: range passes active -- compile-time specialisation keeps
-// the per-tuple instruction count down (the kernel is issue- and L1TEX-wavefront-bound, not HBM-bound).
+
+// per-warp shared-memory ring: tuples are appended with ballot/popc ranks and drained in line-aligned pieces
+template <int CAP>  // power of two; drained CAP/2 tuples at a time
+struct WarpRing {
+    uint2* buf;
+    uint32_t head, count;  // warp-uniform
+    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; }
+    __device__ __forceinline__ void append2(bool fa, uint2 a, bool fb, uint2 b, uint32_t lt) {
+        const uint32_t ma = __ballot_sync(0xffffffffu, fa);
+        const uint32_t mb = __ballot_sync(0xffffffffu, fb);
+        const uint32_t tail = head + count;
+        if (fa) buf[(tail + __popc(ma & lt)) & (CAP - 1)] = a;
+        if (fb) buf[(tail + __popc(ma) + __popc(mb & lt)) & (CAP - 1)] = b;
+        count += __popc(ma) + __popc(mb);
+    }
+    __device__ __forceinline__ void drain(uint32_t cnt, uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol,
+                                          uint32_t lane) {
+        __syncwarp();
+        unsigned long long gb = 0ull;
+        if (lane == 0) gb = atomicAdd(cursor, (unsigned long long)cnt);
+        gb = __shfl_sync(0xffffffffu, gb, 0);
+        for (uint32_t i = lane; i < cnt; i += 32u) st_stream_v2(out + gb + i, buf[(head + i) & (CAP - 1)], pol);
+        head = (head + cnt) & (CAP - 1);
+        count -= cnt;
+        __syncwarp();
+    }
+    // at most 64 tuples are appended between two calls, so one drain of CAP/2 keeps the ring from overflowing
+    __device__ __forceinline__ void drain_if_full(uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol, uint32_t lane) {
+        if (count >= (uint32_t)(CAP / 2)) drain(CAP / 2, out, cursor, pol, lane);
+    }
+};
+
+// MODE bit0: BLOCKED, bit1: single probe (k == 1), bit2: range passes active, bit3: DEFER -- compile-time
+// specialisation keeps the per-tuple instruction count down (the kernel is issue- and L1TEX-wavefront-bound).
+// Range passes with deferral: pass i probes the keys whose first filter bit lies in range i (that part of the filter
+// stays L2-resident) and appends the keys of later ranges to `defer_out`, which is the next pass's input -- S is
+// read from HBM once, later passes read only what is still undecided.
+__host__ __device__ constexpr int kProbeSmemPerWarp(int mode) { return (mode & 8) ? (256 + 512) * 8 : 512 * 8; }
 template <int MODE>
-__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2* __restrict__ S, uint64_t n, BloomParams bp_in,
-                                                                   const uint32_t* __restrict__ g_crc,
+__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2* __restrict__ S, uint64_t n_static,
+                                                                   const unsigned long long* __restrict__ n_ptr,
+                                                                   BloomParams bp_in, const uint32_t* __restrict__ g_crc,
                                                                    uint2* __restrict__ out,
-                                                                   unsigned long long* __restrict__ out_cursor) {
-    constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0;
-    __shared__ __align__(16) uint2 ring_all[kProbeWarps][kWarpRing];
-    __shared__ uint32_t crc_tab[kBlocked ? 1024 : 1];
+                                                                   unsigned long long* __restrict__ out_cursor,
+                                                                   uint2* __restrict__ defer_out,
+                                                                   unsigned long long* __restrict__ defer_cursor) {
+    constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0,
+                   kDefer = (MODE & 8) != 0;
+    constexpr int kSurvCap = kDefer ? 256 : 512;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
     BloomParams bp = bp_in;
     bp.blocked = kBlocked ? 1u : 0u;
     if (kSingle) bp.k = 1u;
@@ -220,25 +279,20 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
         load_crc_tab(crc_tab, g_crc);
         __syncthreads();
     }
+    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    uint2* ring = ring_all[wid];
-    uint32_t head = 0u, count = 0u;  // warp-uniform ring state (tail = head + count)
+    uint2* wsm = reinterpret_cast<uint2*>(smem_raw) + wid * (kProbeSmemPerWarp(MODE) / 8);
+    WarpRing<kSurvCap> surv;
+    surv.init(wsm);
+    WarpRing<512> dfr;
+    dfr.init(wsm + kSurvCap);
     const uint64_t pol = policy_evict_first();
     const uint64_t npairs = n >> 1;
     const uint4* S4 = reinterpret_cast<const uint4*>(S);
     const uint64_t warp_global = (uint64_t)blockIdx.x * kProbeWarps + wid;
     const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
     constexpr uint64_t kPerIter = 32ull * kProbeV;  // pairs per warp iteration
-
-    auto flush = [&](uint32_t cnt) {
-        unsigned long long gb = 0ull;
-        if (lane == 0) gb = atomicAdd(out_cursor, (unsigned long long)cnt);
-        gb = __shfl_sync(0xffffffffu, gb, 0);
-        for (uint32_t i = lane; i < cnt; i += 32u) st_stream_v2(out + gb + i, ring[(head + i) & (kWarpRing - 1)], pol);
-        head = (head + cnt) & (kWarpRing - 1);
-        count -= cnt;
-    };
 
     for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
         const uint64_t p0 = it * kPerIter + lane;
@@ -249,7 +303,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
             t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
         }
         uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
-        bool act[2 * kProbeV];
+        bool act[2 * kProbeV], later[2 * kProbeV];
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
             bool valid = (p0 + (uint64_t)j * 32u) < npairs;
@@ -259,7 +313,9 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
                 uint32_t key = e ? t[j].z : t[j].x;
                 bloom_start(bp, crc_tab, key, base[q], h[q], y[q]);
                 uint32_t a = base[q] + h[q];
-                act[q] = valid && bloom_in_range(bp, a);
+                bool mine = bloom_in_range(bp, a);
+                act[q] = valid && mine;
+                later[q] = kDefer && valid && !mine;  // inputs of pass i only hold ranges >= i
                 w[q] = act[q] ? ld_filter(bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
             }
         }
@@ -268,27 +324,31 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
             bool fa = act[2 * j] && (bp.k == 0u || bloom_test_rest(bp, base[2 * j], h[2 * j], y[2 * j], w[2 * j]));
             bool fb = act[2 * j + 1] &&
                       (bp.k == 0u || bloom_test_rest(bp, base[2 * j + 1], h[2 * j + 1], y[2 * j + 1], w[2 * j + 1]));
-            uint32_t ma = __ballot_sync(0xffffffffu, fa);
-            uint32_t mb = __ballot_sync(0xffffffffu, fb);
-            uint32_t tail = head + count;
-            if (fa) ring[(tail + __popc(ma & lt)) & (kWarpRing - 1)] = make_uint2(t[j].x, t[j].y);
-            if (fb) ring[(tail + __popc(ma) + __popc(mb & lt)) & (kWarpRing - 1)] = make_uint2(t[j].z, t[j].w);
-            count += __popc(ma) + __popc(mb);
-            __syncwarp();
-            if (count >= (uint32_t)kWarpFlush) flush(kWarpFlush);  // <= 64 appended per step, ring never overflows
+            const uint2 ta = make_uint2(t[j].x, t[j].y), tb = make_uint2(t[j].z, t[j].w);
+            surv.append2(fa, ta, fb, tb, lt);
+            surv.drain_if_full(out, out_cursor, pol, lane);
+            if (kDefer) {
+                dfr.append2(later[2 * j], ta, later[2 * j + 1], tb, lt);
+                dfr.drain_if_full(defer_out, defer_cursor, pol, lane);
+            }
         }
     }
-    __syncwarp();
-    if (count) flush(count);
+    if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
+    if (kDefer && dfr.count) dfr.drain(dfr.count, defer_out, defer_cursor, pol, lane);
     // odd tail tuple
     if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {
         uint2 tt = S[n - 1];
         uint32_t b0, h0, y0;
         bloom_start(bp, crc_tab, tt.x, b0, h0, y0);
         uint32_t a = b0 + h0;
-        if (bloom_in_range(bp, a) && (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp.filter + (a >> 5))))) {
-            unsigned long long pos = atomicAdd(out_cursor, 1ull);
-            out[pos] = tt;
+        if (bloom_in_range(bp, a)) {
+            if (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp.filter + (a >> 5)))) {
+                unsigned long long pos = atomicAdd(out_cursor, 1ull);
+                out[pos] = tt;
+            }
+        } else if (kDefer) {
+            unsigned long long pos = atomicAdd(defer_cursor, 1ull);
+            defer_out[pos] = tt;
         }
     }
 }
@@ -379,7 +439,7 @@ __global__ void __launch_bounds__(256) k_owner_hist(const uint2* __restrict__ in
                                                     const uint32_t* __restrict__ g_crc, uint32_t nbins,
                                                     uint32_t* __restrict__ ghist) {
     __shared__ uint32_t wh[8][1 << kMaxLevelBits];
-    __shared__ uint32_t crc_tab[MODE == 4 ? 1024 : 1];
+    __shared__ uint32_t crc_tab[MODE == 4 ? kCrcSmemWords : 1];
     const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
     for (uint32_t i = threadIdx.x; i < 8 * nbins; i += blockDim.x) wh[i / nbins][i % nbins] = 0u;
     if (MODE == 4) load_crc_tab(crc_tab, g_crc);
@@ -449,7 +509,7 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
+__global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
                                                             const uint64_t* __restrict__ n_ptr, uint64_t n_static,
                                                             const uint32_t* __restrict__ fine_off,
                                                             const uint32_t* __restrict__ tile_off,
@@ -466,7 +526,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const uint2* __rest
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
     __shared__ uint8_t sorted_bin[kScatterTile];
-    __shared__ uint32_t crc_tab[MODE == 4 ? 1024 : 1];
+    __shared__ uint32_t crc_tab[MODE == 4 ? kCrcSmemWords : 1];
     const uint32_t wid = threadIdx.x >> 5;
     const uint64_t n = n_ptr ? *n_ptr : n_static;
     const uint32_t b2 = fn.b2;
@@ -659,7 +719,7 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
             if (rb) __syncthreads();
             for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) head[i] = 0u;
             __syncthreads();
-            constexpr int U = 4;  // independent 8-byte loads in flight per thread
+            constexpr int U = HWBRJ_JOIN_UNROLL;  // independent 8-byte loads in flight per thread
             const uint2* Rbase = Rp + (uint64_t)r0 + rb;
             for (uint32_t i0 = threadIdx.x; i0 < cnt; i0 += U * kJoinThreads) {
                 uint2 t[U];

@@ -13,7 +13,7 @@ __device__ __forceinline__ uint32_t crapwow42(uint32_t key) {
     p = (uint64_t)(h ^ (k + n)) * n; h ^= (uint32_t)p; k ^= (uint32_t)(p >> 32);
     return k ^ h;
 }
-enum { S_EVICT_FIRST = 0, S_CS = 1, S_DEFAULT = 2, S_NOALLOC_ONLY = 3 };
+enum { S_EVICT_FIRST = 0, S_CS = 1, S_DEFAULT = 2, S_NOALLOC_ONLY = 3, S_DISCARD = 4, S_LU = 5 };
 enum { P_DEFAULT = 0, P_EVICT_LAST = 1 };
 
 template <int SM>
@@ -25,6 +25,10 @@ __device__ __forceinline__ uint4 lds(const uint4* p, uint64_t pol) {
         asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     else if (SM == S_NOALLOC_ONLY)
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (SM == S_DISCARD) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    } else if (SM == S_LU)
+        asm volatile("ld.global.lu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     else r = *p;
     return r;
 }
@@ -58,6 +62,16 @@ __global__ void __launch_bounds__(256) k_sp(const uint4* __restrict__ S, uint64_
         }
 #pragma unroll
         for (int j = 0; j < 2 * V; j++) cnt += (w[j] >> (h[j] & 31)) & 1u;
+        if (SM == S_DISCARD) {
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                uint64_t idx = i + (uint64_t)j * stride;
+                if (idx < npairs && (threadIdx.x & 7) == 0) {
+                    const void* line = (const void*)((uintptr_t)(S + idx) & ~(uintptr_t)127);
+                    asm volatile("discard.global.L2 [%0], 128;" :: "l"(line) : "memory");
+                }
+            }
+        }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)cnt);
@@ -82,7 +96,7 @@ int main() {
     uint32_t* f; CK(cudaMalloc(&f, 128u << 20)); k_fillf<<<SMS * 8, 256>>>(f, (128u << 20) / 4);
     unsigned long long* out; CK(cudaMalloc(&out, 8)); CK(cudaMemset(out, 0, 8)); CK(cudaDeviceSynchronize());
     // filter is 2^30 bits; active range = 2^lgr bits (probe only keys hashing below it). probes = ns * 2^lgr / 2^30
-    for (int lgr : {27, 28, 29, 30}) {
+    for (int lgr : {29, 30}) {
         uint32_t shift = lgr; double frac = double(1ull << lgr) / double(1ull << 30);
 #define RUN(SM, PM, V, G, name) { float ms = best_of(3, [&] { k_sp<SM, PM, V><<<SMS * G, 256>>>((const uint4*)S, ns / 2, f, 0x3FFFFFFFu, shift, out); }); CK(cudaGetLastError()); \
         printf("active %3d MiB  %-28s v=%d g=%d  %.3f ms  stream %.0f GB/s  probes %.1f G/s\n", (1 << (lgr - 23)), name, V, G, ms, ns * 8 / ms * 1e-6, ns * frac / ms * 1e-6); }
@@ -92,6 +106,8 @@ int main() {
         RUN(S_CS, P_EVICT_LAST, 4, 8, "S .cs, P evict_last");
         RUN(S_NOALLOC_ONLY, P_EVICT_LAST, 4, 8, "S L1 noalloc, P evict_last");
         RUN(S_DEFAULT, P_DEFAULT, 4, 8, "S default, P default");
+        RUN(S_DISCARD, P_DEFAULT, 4, 8, "S evict_first+discard.L2");
+        RUN(S_LU, P_DEFAULT, 4, 8, "S ld.lu (last use)");
         RUN(S_EVICT_FIRST, P_EVICT_LAST, 2, 8, "S evict_first, P evict_last");
         RUN(S_EVICT_FIRST, P_EVICT_LAST, 4, 4, "S evict_first, P evict_last");
     }
