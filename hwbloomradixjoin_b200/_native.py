@@ -51,7 +51,9 @@ EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_la
            "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_host_alloc", "hwbrj_host_free",
            "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_radix_partition",
            "hwbrj_set_stream", "hwbrj_reset_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
-           "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe"]
+           "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe",
+           "hwbrj_rel_wrap_counted", "hwbrj_symm_alloc", "hwbrj_symm_free", "hwbrj_ipc_export", "hwbrj_ipc_open",
+           "hwbrj_ipc_close", "hwbrj_route_peer", "hwbrj_filter_probe_async"]
 
 _lib = None
 
@@ -105,6 +107,17 @@ def load():
     L.hwbrj_set_device.argtypes = [C.c_int]
     L.hwbrj_rel_wrap.restype = C.c_void_p
     L.hwbrj_rel_wrap.argtypes = [C.c_void_p, C.c_uint64]
+    L.hwbrj_rel_wrap_counted.restype = C.c_void_p
+    L.hwbrj_rel_wrap_counted.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.hwbrj_symm_alloc.restype = C.c_void_p
+    L.hwbrj_symm_alloc.argtypes = [C.c_uint64]
+    L.hwbrj_symm_free.argtypes = [C.c_void_p]
+    L.hwbrj_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.hwbrj_ipc_open.restype = C.c_void_p
+    L.hwbrj_ipc_open.argtypes = [C.c_void_p]
+    L.hwbrj_ipc_close.argtypes = [C.c_void_p]
+    L.hwbrj_route_peer.argtypes = [C.c_void_p, C.c_int, argp, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.hwbrj_filter_probe_async.argtypes = [C.c_void_p, C.c_void_p, argp, C.c_void_p, C.c_void_p]
     L.hwbrj_rel_ptr.restype = C.c_void_p
     L.hwbrj_rel_ptr.argtypes = [C.c_void_p]
     L.hwbrj_rel_generate_shard.restype = C.c_void_p

@@ -24,7 +24,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
     from . import BloomFilterArgs
-    from .dist import CudaOps, dist_join
+    from .dist import CudaOps, PeerFabric, dist_join, dist_join_peer
     ops = CudaOps(device)
     r, s, q, variant, m, k, B, desc = wl
     bloom = BloomFilterArgs(variant, m, k, B) if variant is not None else None
@@ -38,8 +38,21 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     Rsh = ops.generate_shard(0, r, r, 1.0, 1, rlo, rcnt)
     Ssh = ops.generate_shard(1, s, r, q, 2, slo, scnt)
 
+    # exchanges fused into the partitioning kernels (NVLink peer stores); NCCL all-to-all is the fallback
+    use_peer = os.environ.get("HWBRJ_DIST_PATH", "peer") == "peer"
+    fabric = PeerFabric(ops, int(r / world * 1.2) + 65536, int(s / world * 1.2) + 65536) if use_peer else None
+
+    def step(Rt, St, time_phases=False):
+        if fabric is not None:
+            out = dist_join_peer(ops, fabric, Rt, St, bloom, r, s, time_phases=time_phases)
+            if out is not None:
+                return out
+        out = dist_join(ops, Rt, St, bloom, time_phases=time_phases)
+        out["path"] = "nccl-all-to-all"
+        return out
+
     for _ in range(max(args.warmup, 3)):
-        res = dist_join(ops, Rsh, Ssh, bloom)
+        res = step(Rsh, Ssh)
     sampler = ClockSampler(local)
     dist.barrier()
     torch.cuda.synchronize()
@@ -49,7 +62,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        res = dist_join(ops, Rsh, Ssh, bloom)
+        res = step(Rsh, Ssh)
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -59,7 +72,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
     ms_per_step = ms.item() / args.steps
     value = (r + s) / (ms_per_step * 1e-3) / 1e6
-    phased = dist_join(ops, Rsh, Ssh, bloom, time_phases=True)
+    phased = step(Rsh, Ssh, time_phases=True)
 
     # ---- host-buffer leg: pinned host shards -> device, collective join, scalars back ----
     e2e_steps = args.e2e_steps or min(args.steps, 5)
@@ -72,7 +85,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     def host_step():
         dR.copy_(hR, non_blocking=True)
         dS.copy_(hS, non_blocking=True)
-        return dist_join(ops, dR, dS, bloom)
+        return step(dR, dS)
     host_step()
     dist.barrier()
     torch.cuda.synchronize()
@@ -98,14 +111,15 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
                                    "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / (peak * world)}}
         if roofline["achieved"]:
             roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        nvl_bytes = 8 * (res["tuples_over_nvlink_r"] + res["tuples_over_nvlink_s"]) + \
-            (world - 1) * (m // 8 if bloom is not None else 0) * (1 if res["sliced_filter"] else world)
+        moved = (r + F) * (world - 1) // world  # hash owners: (G-1)/G of R and of the survivors leave their rank
+        nvl_bytes = 8 * moved + (world - 1) * (m // 8 if bloom is not None else 0) * (1 if res["sliced_filter"] else world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q,
                            "bloom": None if bloom is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
                            "sharding": "contiguous chunks per rank; owner = filter-slice rank" if res["sliced_filter"] else "contiguous chunks per rank; owner = crapwow top bits",
+                           "exchange": res.get("path", "nccl-all-to-all"),
                            "l2": "per-rank inputs exceed the 126 MB L2; no flush needed"},
                 "results": {"matches": res["matches"], "filtered": res["filtered"], "checksum_pair": res["checksum_pair"]},
                 "phases_ms_rank0": ph, "wall_ms_per_step": wall / args.steps * 1e3, "nvlink_bytes_total": nvl_bytes,
@@ -115,6 +129,8 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
                         "api": "hwbloomradixjoin_b200.dist.dist_join on pinned host shards"},
                 "gpu_launches": int(args.steps * world * (phased["local"]["kernel_launches"] + 8)), "clocks": clocks}
         print(json.dumps(line))
+    if fabric is not None:
+        fabric.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0

@@ -315,11 +315,14 @@ static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t
 
 // The join on device-resident relations. args == nullptr: plain radix join.
 static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS, const bloom_filter_args_t* args,
-                     hwbrj_stats_t& st) {
+                     hwbrj_stats_t& st, const unsigned long long* nR_dev = nullptr, uint64_t nR_expect = 0,
+                     const unsigned long long* nS_dev = nullptr) {
+    // nR/nS are exact counts, or capacities when the real counts live on the device (nR_dev/nS_dev)
     if (nR >= (1ull << 32) || nS >= (1ull << 32)) die("relations of 2^32 or more tuples are not supported");
     if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
+    if (args && nS_dev) die("device-side S count is only supported for the filter-less join");
     ensure_workspace(nR, nS, args);
-    const int bits = pick_bits(nR);
+    const int bits = pick_bits(nR_dev ? nR_expect : nR);
     const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
     const uint32_t P = 1u << bits;
     const uint32_t pmask = P - 1u;
@@ -347,19 +350,19 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
         for (int r = 0; r < nranges; r++) {
             bp.range_id = (uint32_t)r;
-            k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nullptr, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+            k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
             launches++;
         }
     } else {
-        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nullptr, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
         launches++;
     }
     CK(cudaEventRecord(g.ev[2], g.stream));
-    const uint2* Rp = run_partition(dR, nR, nullptr, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(),
+    const uint2* Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(),
                                     g.rt1.as<uint2>(), g.rp.as<uint2>(), launches);
     CK(cudaEventRecord(g.ev[3], g.stream));
     const uint2* Sin = dS;
-    const unsigned long long* n_dev = nullptr;
+    const unsigned long long* n_dev = nS_dev;
     if (args) {
         if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(nS, 1) * 8);
         launches += run_probe(dS, nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
@@ -528,8 +531,10 @@ int hwbrj_check_args(const bloom_filter_args_t* args) { return args ? check_args
 
 struct hwbrj_rel {
     uint2* d;
-    uint64_t n;
+    uint64_t n;                        // tuple count, or capacity / upper bound when n_dev is set
     bool owned;
+    const unsigned long long* n_dev;   // optional: the real count lives on the device (no host round trip)
+    uint64_t n_expect;                 // sizing hint when n_dev is set
 };
 
 hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
@@ -538,6 +543,8 @@ hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
     hwbrj_rel_t* r = new hwbrj_rel;
     r->n = n;
     r->owned = true;
+    r->n_dev = nullptr;
+    r->n_expect = n;
     CK(cudaMalloc(&r->d, std::max<uint64_t>(n, 2) * 8 + 64));
     if (n) CK(cudaMemcpy(r->d, tuples, n * 8, cudaMemcpyHostToDevice));
     return r;
@@ -556,6 +563,8 @@ hwbrj_rel_t* hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double q
     hwbrj_rel_t* rel = new hwbrj_rel;
     rel->n = count;
     rel->owned = true;
+    rel->n_dev = nullptr;
+    rel->n_expect = count;
     CK(cudaMalloc(&rel->d, std::max<uint64_t>(count, 2) * 8 + 64));
     if (count) {
         // generator.c:344: ntuples_above = num_tuples * (1 - selectivity)
@@ -588,6 +597,14 @@ hwbrj_rel_t* hwbrj_rel_wrap(void* device_tuples, uint64_t n) {
     r->d = reinterpret_cast<uint2*>(device_tuples);
     r->n = n;
     r->owned = false;
+    r->n_dev = nullptr;
+    r->n_expect = n;
+    return r;
+}
+hwbrj_rel_t* hwbrj_rel_wrap_counted(void* device_tuples, uint64_t capacity, const void* d_count, uint64_t expected) {
+    hwbrj_rel_t* r = hwbrj_rel_wrap(device_tuples, capacity);
+    r->n_dev = reinterpret_cast<const unsigned long long*>(d_count);
+    r->n_expect = expected;
     return r;
 }
 void* hwbrj_rel_ptr(const hwbrj_rel_t* rel) { return rel ? rel->d : nullptr; }
@@ -622,7 +639,7 @@ int hwbrj_join_device(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_fi
     if (!R || !S) return -1;
     hwbrj_stats_t st;
     memset(&st, 0, sizeof(st));
-    run_join(R->d, R->n, S->d, S->n, args, st);
+    run_join(R->d, R->n, S->d, S->n, args, st, R->n_dev, R->n_expect, S->n_dev);
     g.last = st;
     if (out) *out = st;
     return 0;
@@ -806,6 +823,109 @@ int hwbrj_owner_partition(const hwbrj_rel_t* in, int world, const bloom_filter_a
     return 0;
 }
 
+// ---- peer memory (CUDA IPC) and the fused partition + all-to-all ---------------------------------------------------
+void* hwbrj_symm_alloc(uint64_t bytes) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    void* p = nullptr;
+    CK(cudaMalloc(&p, std::max<uint64_t>(bytes, 256)));
+    CK(cudaMemset(p, 0, std::max<uint64_t>(bytes, 256)));
+    return p;
+}
+void hwbrj_symm_free(void* p) {
+    if (p) cudaFree(p);
+}
+int hwbrj_ipc_export(void* p, void* handle_out) {
+    init_ctx();
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    static_assert(sizeof(h) == HWBRJ_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+void* hwbrj_ipc_open(const void* handle) {
+    init_ctx();
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+int hwbrj_ipc_close(void* p) {
+    if (p && cudaIpcCloseMemHandle(p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return 0;
+}
+
+int hwbrj_route_peer(const hwbrj_rel_t* in, int world, const bloom_filter_args_t* slice_args, void* const* peer_bufs,
+                     void* const* peer_cursors, uint64_t capacity_tuples, void* d_overflow_flag) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!in || world < 1 || world > kMaxPeers || (world & (world - 1)) || in->n >= (1ull << 32)) return -1;
+    if (slice_args && check_args_impl(slice_args, true)) return -1;
+    if (slice_args && slice_args->variant == BASIC && slice_args->k > 1) slice_args = nullptr;
+    ensure_workspace(1, 1, nullptr);
+    int mode = 3;
+    BinFn fn = owner_fn(world, slice_args, mode);
+    PeerTargets pt;
+    memset(&pt, 0, sizeof(pt));
+    for (int i = 0; i < world; i++) {
+        pt.buf[i] = reinterpret_cast<uint2*>(peer_bufs[i]);
+        pt.cursor[i] = reinterpret_cast<unsigned long long*>(peer_cursors[i]);
+    }
+    pt.capacity = capacity_tuples;
+    pt.overflow = reinterpret_cast<unsigned int*>(d_overflow_flag);
+    const uint64_t* n_ptr = reinterpret_cast<const uint64_t*>(in->n_dev);
+    static int occ3 = 0, occ4 = 0;
+    if (!occ3) {
+        CK(cudaFuncSetAttribute(k_scatter<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+        CK(cudaFuncSetAttribute(k_scatter<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_scatter<3, true>, kScatterThreads, kScatterSmem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_scatter<4, true>, kScatterThreads, kScatterSmem));
+        occ3 = std::max(occ3, 1);
+        occ4 = std::max(occ4, 1);
+    }
+    if (mode == 4)
+        k_scatter<4, true><<<g.sms * occ4, kScatterThreads, kScatterSmem, g.stream>>>(
+            in->d, nullptr, n_ptr, in->n, nullptr, nullptr, nullptr, fn, g.d_crc, (uint32_t)world, pt);
+    else
+        k_scatter<3, true><<<g.sms * occ3, kScatterThreads, kScatterSmem, g.stream>>>(
+            in->d, nullptr, n_ptr, in->n, nullptr, nullptr, nullptr, fn, g.d_crc, (uint32_t)world, pt);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// probe that leaves the survivor count on the device (no host round trip): count_out is a device u64, zeroed here
+int hwbrj_filter_probe_async(const void* d_filter, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out,
+                             void* d_count_out) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!S || !args || !d_filter || !d_out || !d_count_out || check_args_impl(args, true)) return -1;
+    g.ctrl.ensure(sizeof(Control));
+    g.st1.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    CK(cudaMemsetAsync(d_count_out, 0, 8, g.stream));
+    BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(const_cast<void*>(d_filter)));
+    int nranges = pick_ranges(args);
+    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    const int base_mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0);
+    bp.nranges = (uint32_t)nranges;
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        launch_probe_mode(base_mode | (nranges > 1 ? 4 : 0), S->d, S->n, S->n_dev, bp, reinterpret_cast<uint2*>(d_out),
+                          reinterpret_cast<unsigned long long*>(d_count_out), nullptr, nullptr);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int hwbrj_filter_build(const hwbrj_rel_t* R, const bloom_filter_args_t* args, void* d_filter, int zero_first) {
     std::lock_guard<std::mutex> lock(g.mu);
     init_ctx();
@@ -819,7 +939,7 @@ int hwbrj_filter_build(const hwbrj_rel_t* R, const bloom_filter_args_t* args, vo
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, nullptr, bp, g.d_crc,
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, R->n_dev, bp, g.d_crc,
                                                                           g.histR.as<uint32_t>(), 0u);
     }
     CK(cudaGetLastError());

@@ -12,6 +12,7 @@
 namespace hwbrj {
 
 constexpr int kMaxLevelBits = 7;                     // radix bits per scatter pass
+constexpr int kMaxPeers = 16;                        // GPUs of one NVLink domain
 constexpr int kMaxRadixBits = 2 * kMaxLevelBits;     // 2 passes
 constexpr int kTableCap = 8192;                      // R tuples per shared-memory hash table
 #ifndef HWBRJ_JOIN_THREADS
@@ -508,13 +509,24 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
     return it;
 }
 
-template <int MODE>
+// REMOTE (multi-GPU, fused partition + all-to-all): bin g is owner GPU g; its run is claimed from GPU g's cursor with a
+// system-scope atomic over NVLink and stored straight into GPU g's receive buffer (peer memory), so the exchange
+// needs neither send buffers, counts on the host, nor a separate collective.
+struct PeerTargets {
+    uint2* buf[kMaxPeers];                  // receive buffers (peer device pointers mapped into this process)
+    unsigned long long* cursor[kMaxPeers];  // tuples received so far, lives on the owner
+    unsigned long long capacity;            // tuples per receive buffer
+    unsigned int* overflow;                 // local flag, set when a claim does not fit
+};
+
+template <int MODE, bool REMOTE = false>
 __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
                                                             const uint64_t* __restrict__ n_ptr, uint64_t n_static,
                                                             const uint32_t* __restrict__ fine_off,
                                                             const uint32_t* __restrict__ tile_off,
                                                             uint32_t* __restrict__ cursor, BinFn fn,
-                                                            const uint32_t* __restrict__ g_crc, uint32_t nbins) {
+                                                            const uint32_t* __restrict__ g_crc, uint32_t nbins,
+                                                            PeerTargets peers = PeerTargets()) {
     constexpr int NW = kScatterThreads / 32;
     constexpr int PER = kScatterTile / kScatterThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -522,7 +534,7 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
     uint2* sorted = raw + kScatterStages * kScatterStageTuples;            // [kScatterTile]
     __shared__ uint32_t whist[NW][1 << kMaxLevelBits];
     __shared__ uint32_t binstart[1 << kMaxLevelBits];
-    __shared__ uint32_t gclaim[1 << kMaxLevelBits];
+    __shared__ unsigned long long gclaim[REMOTE ? kMaxPeers : (1 << kMaxLevelBits)];
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
     __shared__ uint8_t sorted_bin[kScatterTile];
@@ -585,7 +597,16 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
                 tot += c;
             }
             binstart[threadIdx.x] = tot;
-            gclaim[threadIdx.x] = tot ? atomicAdd(&cursor[d.cbase + threadIdx.x], tot) : 0u;
+            if (REMOTE) {
+                unsigned long long c = tot ? atomicAdd_system(peers.cursor[threadIdx.x], (unsigned long long)tot) : 0ull;
+                if (c + tot > peers.capacity) {  // does not fit: flag it and drop the run (the host falls back)
+                    atomicExch(peers.overflow, 1u);
+                    c = ~0ull;
+                }
+                gclaim[threadIdx.x] = c;
+            } else {
+                gclaim[threadIdx.x] = tot ? atomicAdd(&cursor[d.cbase + threadIdx.x], tot) : 0u;
+            }
         }
         __syncthreads();  // (B)
         if (threadIdx.x < 32) {  // exclusive scan over nbins (<=128) totals: 4 per lane
@@ -624,7 +645,12 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
         __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
             uint32_t bin = sorted_bin[i];
-            out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = sorted[i];
+            if (REMOTE) {
+                unsigned long long c = gclaim[bin];
+                if (c != ~0ull) peers.buf[bin][c + (i - binstart[bin])] = sorted[i];  // NVLink store (or local)
+            } else {
+                out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = sorted[i];
+            }
         }
         // next iteration: whist is rewritten before (A'), binstart/gclaim after (A'), sorted after (C'): no
         // thread can pass (A') before every thread has finished this write-out loop

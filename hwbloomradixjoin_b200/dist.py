@@ -59,6 +59,12 @@ class CudaOps:
     def _wrap(self, t: torch.Tensor) -> int:
         return self.L.hwbrj_rel_wrap(t.data_ptr(), t.numel())
 
+    def view_int64(self, ptr: int, n: int) -> torch.Tensor:
+        """torch view of library-owned device memory (plumbing for zeroing / reading small control words)"""
+        class _View:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        return torch.as_tensor(_View(), device=self.device)
+
     def generate_shard(self, kind: int, n: int, r: int, q: float, seed: int, begin: int, count: int) -> torch.Tensor:
         h = self.L.hwbrj_rel_generate_shard(kind, n, r, q, seed, begin, count)
         out = self.empty_tuples(count)
@@ -239,3 +245,164 @@ def dist_join(ops, Rshard: torch.Tensor, Sshard: torch.Tensor, bloom: Optional[B
     return {"matches": vals[0], "filtered": vals[1] if bloom is not None else -1, "checksum_pair": vals[2],
             "checksum_rpay": vals[3], "checksum_spay": vals[4], "checksum_key": vals[5],
             "tuples_over_nvlink_r": vals[6], "tuples_over_nvlink_s": vals[7], "local": st, **info}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# NVLink peer-memory path: the exchanges are done BY the partitioning kernel (fused partition + all-to-all)
+# ----------------------------------------------------------------------------------------------------------------
+class PeerFabric:
+    """Per-rank receive buffers that every peer of the NVLink domain can store into.
+
+    The buffers are allocated by the library (cudaMalloc) and exported as CUDA IPC handles; the 64-byte handles
+    travel through torch.distributed and each rank maps its peers' buffers. `hwbrj_route_peer` then writes every
+    tuple straight into its owner's buffer, claiming space from the owner's cursor with a system-scope atomic over
+    NVLink: no send buffers, no counts on the host, no collective for the data. Ranks are separated by tiny
+    stream-ordered all-reduces (route -> consume)."""
+
+    CTRL_BYTES = 256  # [0] R cursor u64, [1] S cursor u64, [2] overflow u32, rest reserved
+
+    def __init__(self, ops: "CudaOps", cap_r: int, cap_s: int, group=None):
+        self.ops, self.group = ops, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap_r, self.cap_s = int(cap_r), int(cap_s)
+        L = ops.L
+        self.local = [L.hwbrj_symm_alloc((self.cap_r + 8) * 8), L.hwbrj_symm_alloc((self.cap_s + 8) * 8),
+                      L.hwbrj_symm_alloc(self.CTRL_BYTES)]
+        if not all(self.local):
+            raise RuntimeError("hwbrj_symm_alloc failed")
+        handles = torch.zeros(3 * N_IPC, dtype=torch.uint8)
+        for i, p in enumerate(self.local):
+            buf = (C.c_ubyte * N_IPC)()
+            if L.hwbrj_ipc_export(p, buf) != 0:
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+            handles[i * N_IPC:(i + 1) * N_IPC] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+        handles = handles.to(ops.device)
+        allh = [torch.empty_like(handles) for _ in range(self.world)]
+        dist.all_gather(allh, handles, group=group)
+        self.peer = []  # peer[g] = [recvR, recvS, ctrl] pointers valid in this process
+        for g in range(self.world):
+            if g == self.rank:
+                self.peer.append(list(self.local))
+                continue
+            hb = allh[g].cpu().numpy().tobytes()
+            ptrs = []
+            for i in range(3):
+                raw = (C.c_ubyte * N_IPC).from_buffer_copy(hb[i * N_IPC:(i + 1) * N_IPC])
+                p = L.hwbrj_ipc_open(raw)
+                if not p:
+                    raise RuntimeError(f"cudaIpcOpenMemHandle failed for rank {g}")
+                ptrs.append(p)
+            self.peer.append(ptrs)
+        self._bar = torch.zeros(1, dtype=torch.int32, device=ops.device)
+        self.ctrl_view = ops.view_int64(self.local[2], self.CTRL_BYTES // 8)
+        self.barrier()
+
+    def barrier(self):
+        """stream-ordered barrier across ranks (no host synchronisation)"""
+        dist.all_reduce(self._bar, group=self.group)
+
+    def ptr_array(self, which: int, byte_offset: int = 0):
+        arr = (C.c_void_p * self.world)()
+        for g in range(self.world):
+            arr[g] = self.peer[g][which] + byte_offset
+        return arr
+
+    def reset(self):
+        self.ctrl_view.zero_()
+        self.barrier()  # nobody routes into a rank that has not zeroed its cursors yet
+
+    def close(self):
+        L = self.ops.L
+        torch.cuda.synchronize()
+        self.barrier()
+        torch.cuda.synchronize()
+        for g in range(self.world):
+            if g != self.rank:
+                for p in self.peer[g]:
+                    L.hwbrj_ipc_close(p)
+        self.barrier()
+        torch.cuda.synchronize()
+        for p in self.local:
+            L.hwbrj_symm_free(p)
+
+
+N_IPC = 64  # HWBRJ_IPC_HANDLE_BYTES
+
+
+def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Sshard: torch.Tensor,
+                   bloom: Optional[BloomFilterArgs], r_total: int, s_total: int, time_phases: bool = False) -> Optional[dict]:
+    """Collective join with the exchanges fused into the partitioning kernels (NVLink peer stores). Returns None when
+    a receive buffer overflowed (heavily skewed owners): the caller then uses dist_join (NCCL all-to-all)."""
+    if bloom is not None:
+        bloom.check()
+    group, world, rank = fabric.group, fabric.world, fabric.rank
+    L = ops.L
+    is_sliced = sliceable(bloom, world)
+    slice_args = bloom if is_sliced else None
+    cargs = slice_args.to_c() if slice_args is not None else None
+    cref = C.byref(cargs) if cargs is not None else None
+    tm = PhaseTimer(time_phases)
+    ctrl = fabric.local[2]
+    tm.mark("start")
+    fabric.reset()
+    tm.mark("reset_barrier")
+    # (1) R: fused partition + all-to-all
+    h = ops._wrap(Rshard)
+    rc = L.hwbrj_route_peer(h, world, cref, fabric.ptr_array(0), fabric.ptr_array(2, 0), fabric.cap_r, ctrl + 16)
+    L.hwbrj_rel_free(h)
+    if rc != 0:
+        raise RuntimeError("hwbrj_route_peer(R) failed")
+    fabric.barrier()
+    tm.mark("route_r_fused")
+    Rown = L.hwbrj_rel_wrap_counted(fabric.local[0], fabric.cap_r, ctrl, max(r_total // world, 1))
+    # (2) filter slice / partial + combine, (3) local pre-filter
+    if bloom is not None:
+        filt = torch.empty(max(bloom.m // 8, 16), dtype=torch.uint8, device=ops.device)
+        bc = bloom.to_c()
+        if L.hwbrj_filter_build(Rown, C.byref(bc), filt.data_ptr(), 1) != 0:
+            raise RuntimeError("hwbrj_filter_build failed")
+        tm.mark("filter_build")
+        filt = combine_filter(ops, filt, bloom, is_sliced, group)
+        tm.mark("filter_all_gather")
+        surv = ops.empty_tuples(Sshard.numel())
+        cnt = torch.zeros(1, dtype=torch.int64, device=ops.device)
+        hs = ops._wrap(Sshard)
+        if L.hwbrj_filter_probe_async(filt.data_ptr(), hs, C.byref(bc), surv.data_ptr(), cnt.data_ptr()) != 0:
+            raise RuntimeError("hwbrj_filter_probe_async failed")
+        L.hwbrj_rel_free(hs)
+        tm.mark("s_probe")
+        hsurv = L.hwbrj_rel_wrap_counted(surv.data_ptr(), surv.numel(), cnt.data_ptr(), surv.numel())
+    else:
+        cnt = None
+        hsurv = ops._wrap(Sshard)
+    # (4) survivors: fused partition + all-to-all
+    rc = L.hwbrj_route_peer(hsurv, world, cref, fabric.ptr_array(1), fabric.ptr_array(2, 8), fabric.cap_s, ctrl + 16)
+    L.hwbrj_rel_free(hsurv)
+    if rc != 0:
+        raise RuntimeError("hwbrj_route_peer(S) failed")
+    fabric.barrier()
+    tm.mark("route_s_fused")
+    # (5) local join of owned R and owned survivors; counts stay on the device
+    Sown = L.hwbrj_rel_wrap_counted(fabric.local[1], fabric.cap_s, ctrl + 8, max(s_total // world, 1))
+    st = N.StatsT()
+    rc = L.hwbrj_join_device(Rown, Sown, None, C.byref(st))  # synchronises the stream to fetch the scalars
+    L.hwbrj_rel_free(Rown)
+    L.hwbrj_rel_free(Sown)
+    if rc != 0:
+        raise RuntimeError("hwbrj_join_device failed")
+    tm.mark("local_join")
+    c = fabric.ctrl_view.tolist()
+    filtered_local = int(cnt.item()) if cnt is not None else 0
+    overflow = c[2] & 0xFFFFFFFF
+    vals = _reduce_scalars([st.matches, filtered_local, st.checksum_pair, st.checksum_rpay, st.checksum_spay,
+                            st.checksum_key, overflow, c[0], c[1]], ops.device, group)
+    if vals[6]:
+        return None
+    out = {"matches": vals[0], "filtered": vals[1] if bloom is not None else -1, "checksum_pair": vals[2],
+           "checksum_rpay": vals[3], "checksum_spay": vals[4], "checksum_key": vals[5], "sliced_filter": is_sliced,
+           "world": world, "r_owned_total": vals[7], "s_owned_total": vals[8], "local": st.as_dict(),
+           "path": "nvlink-peer-stores"}
+    if tm.enabled:
+        torch.cuda.synchronize()
+        out["phases_ms"] = tm.phases_ms()
+    return out

@@ -190,6 +190,9 @@ void hwbrj_reset_stream(void);             /* back to the library's own stream *
 int  hwbrj_sync(void);
 int  hwbrj_set_device(int device);           /* before the first call: one process per GPU */
 hwbrj_rel_t * hwbrj_rel_wrap(void * device_tuples, uint64_t n); /* non-owning view of device memory */
+/* same, but the real tuple count is a device-resident uint64 (written by an earlier kernel): `capacity` bounds it,
+ * `expected` sizes the radix fan-out. Lets a pipeline run without host round trips. */
+hwbrj_rel_t * hwbrj_rel_wrap_counted(void * device_tuples, uint64_t capacity, const void * d_count, uint64_t expected);
 void *        hwbrj_rel_ptr(const hwbrj_rel_t * rel);
 /* positions [begin, begin+count) of the global generated relation (a rank's contiguous input chunk, the GPU
  * analogue of the per-thread chunks of parallel_radix_join_bloom.c:1646-1672) */
@@ -200,6 +203,23 @@ hwbrj_rel_t * hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double 
  * top bits of crapwow(42,key); equal keys always share an owner, so owners join independently. */
 int hwbrj_owner_partition(const hwbrj_rel_t * in, int world, const bloom_filter_args_t * slice_args, void * d_out,
                           uint64_t * counts_out);
+/* peer memory: buffers other ranks of the NVLink domain write into. The 64-byte handles travel through the host's
+ * own channel (e.g. torch.distributed.all_gather) and are opened by every peer. */
+#define HWBRJ_IPC_HANDLE_BYTES 64
+void * hwbrj_symm_alloc(uint64_t bytes); /* zero-initialised device memory that can be exported */
+void   hwbrj_symm_free(void * p);
+int    hwbrj_ipc_export(void * p, void * handle_out /* HWBRJ_IPC_HANDLE_BYTES */);
+void * hwbrj_ipc_open(const void * handle);
+int    hwbrj_ipc_close(void * p);
+/* fused partition-by-owner + all-to-all: every tuple of `in` is stored straight into its owner's receive buffer
+ * (peer_bufs[g], capacity_tuples each) at a position claimed from the owner's cursor (peer_cursors[g], uint64) with
+ * a system-scope atomic over NVLink. A claim that does not fit sets *d_overflow_flag (uint32) and is dropped.
+ * The caller separates routing from consumption with a stream-ordered barrier across ranks. */
+int hwbrj_route_peer(const hwbrj_rel_t * in, int world, const bloom_filter_args_t * slice_args, void * const * peer_bufs,
+                     void * const * peer_cursors, uint64_t capacity_tuples, void * d_overflow_flag);
+/* hwbrj_filter_probe without the host round trip: the survivor count is left in *d_count_out (device uint64) */
+int hwbrj_filter_probe_async(const void * d_filter, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
+                             void * d_out, void * d_count_out);
 /* insert R's keys into the full-size filter at d_filter (m/8 bytes, device) */
 int hwbrj_filter_build(const hwbrj_rel_t * R, const bloom_filter_args_t * args, void * d_filter, int zero_first);
 /* dst |= src over nbytes (multiple of 16): combines partial filters (NCCL has no bitwise-OR reduction) */

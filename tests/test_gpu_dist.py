@@ -18,18 +18,30 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 from hwbloomradixjoin_b200 import BloomFilterArgs
-from hwbloomradixjoin_b200.dist import CudaOps, dist_join
+from hwbloomradixjoin_b200.dist import CudaOps, PeerFabric, dist_join, dist_join_peer
 ops = CudaOps(dev)
 r, s, q = 2_000_000, 16_000_000, 0.01
 per_r, per_s = r // world, s // world
 R = ops.generate_shard(0, r, r, 1.0, 1, rank * per_r, r - rank * per_r if rank == world - 1 else per_r)
 S = ops.generate_shard(1, s, r, q, 2, rank * per_s, s - rank * per_s if rank == world - 1 else per_s)
-out = []
+out, peer = [], []
+fabric = PeerFabric(ops, int(r / world * 1.25) + 65536, int(s / world * 1.25) + 65536)
 for case in [(0, 1 << 24, 1, 512), (0, 1 << 24, 3, 512), (1, 1 << 24, 4, 256), None]:
-    res = dist_join(ops, R, S, BloomFilterArgs(*case) if case else None)
+    bloom = BloomFilterArgs(*case) if case else None
+    res = dist_join(ops, R, S, bloom)
     out.append({k: res[k] for k in ("matches", "filtered", "checksum_pair", "checksum_key", "sliced_filter", "tuples_over_nvlink_s")})
+    for rep in range(2):  # twice: the cursors must be reset correctly between joins
+        pres = dist_join_peer(ops, fabric, R, S, bloom, r, s)
+    peer.append({k: pres[k] for k in ("matches", "filtered", "checksum_pair", "checksum_key", "r_owned_total", "s_owned_total")})
+# a receive buffer that is too small must be reported (None), never silently truncate
+small = PeerFabric(ops, 1000, 1000)
+overflowed = dist_join_peer(ops, small, R, S, None, r, s) is None
+small.close()
+fabric.close()
 if rank == 0:
     print("RESULT " + json.dumps(out))
+    print("PEER " + json.dumps(peer))
+    print("OVERFLOW " + json.dumps(overflowed))
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -47,6 +59,8 @@ def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")][0]
     got = json.loads(line[7:])
+    peer = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("PEER ")][0][5:])
+    assert json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("OVERFLOW ")][0][9:]) is True
     r, s, q = 2_000_000, 16_000_000, 0.01
     dR = Hgpu.DeviceRelation.generate(0, r, r, 1.0, 1)
     dS = Hgpu.DeviceRelation.generate(1, s, r, q, 2)
@@ -56,3 +70,8 @@ def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path):
                (one.totalresults, one.filtered, one.checksum_pair, one.checksum_key), case
         if case:
             assert g["tuples_over_nvlink_s"] <= one.filtered
+    for case, g in zip([(0, 1 << 24, 1, 512), (0, 1 << 24, 3, 512), (1, 1 << 24, 4, 256), None], peer):
+        one = Hgpu.join_device(dR, dS, Hgpu.BloomFilterArgs(*case) if case else None)
+        assert (g["matches"], g["filtered"], g["checksum_pair"], g["checksum_key"]) == \
+               (one.totalresults, one.filtered, one.checksum_pair, one.checksum_key), ("peer path", case)
+        assert g["r_owned_total"] == r and g["s_owned_total"] == (one.filtered if case else s)
