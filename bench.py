@@ -43,6 +43,16 @@ METRIC = "M input tuples/s ((|R|+|S|)/time)"
 UNIT = "Mtuples/s"
 
 
+def ncu_traffic(kernel_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json; null when there is no capture for this workload)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -67,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -166,7 +176,7 @@ def run_reference_arm(args, wl_name, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
@@ -230,7 +240,8 @@ def main():
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     b_alg = (24 * r + 8 * s + 16 * F + 2 * (m // 8)) if bloom is not None else (24 * r + 24 * s)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(f"{args.workload}:{'k_probe_compact' if bloom is not None else 'k_scatter'}"),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_set": dom_bytes, "ms_per_launch_set": dom_ms,
                 "launches_per_step": stats[-1]["range_passes"] if bloom is not None else 1,
                 "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,

@@ -20,6 +20,9 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
         if rank == 0:
             print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with one rank per GPU"}))
         return 1
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything else goes to stderr
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
@@ -128,7 +131,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
                         "d2h_bytes_per_step": 8 * 16 * world, "ms_per_step": e2e_t.item() * 1e3, "steps": e2e_steps,
                         "api": "hwbloomradixjoin_b200.dist.dist_join on pinned host shards"},
                 "gpu_launches": int(args.steps * world * (phased["local"]["kernel_launches"] + 8)), "clocks": clocks}
-        print(json.dumps(line))
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     if fabric is not None:
         fabric.close()
     dist.barrier()

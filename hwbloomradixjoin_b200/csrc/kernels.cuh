@@ -31,7 +31,7 @@ constexpr int kTableCap = 8192;                      // R tuples per shared-memo
 #define HWBRJ_SCATTER_STAGES 2
 #endif
 #ifndef HWBRJ_SCATTER_MINBLOCKS
-#define HWBRJ_SCATTER_MINBLOCKS 1
+#define HWBRJ_SCATTER_MINBLOCKS 4
 #endif
 constexpr int kJoinThreads = HWBRJ_JOIN_THREADS;
 constexpr int kSChunk = 32768;                       // S tuples per join work item
@@ -527,19 +527,20 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
                                                             uint32_t* __restrict__ cursor, BinFn fn,
                                                             const uint32_t* __restrict__ g_crc, uint32_t nbins,
                                                             PeerTargets peers = PeerTargets()) {
-    constexpr int NW = kScatterThreads / 32;
     constexpr int PER = kScatterTile / kScatterThreads;
+    constexpr int NB = 1 << kMaxLevelBits;
+    constexpr bool kKeepBin = MODE >= 3;  // hash owners: remember the bin; radix bins are recomputed from the key
+    static_assert(kScatterThreads >= 32 + NB, "claims run on threads 32.. beside the scan warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* raw = reinterpret_cast<uint2*>(smem_raw);                       // [stages][kScatterStageTuples]
     uint2* sorted = raw + kScatterStages * kScatterStageTuples;            // [kScatterTile]
-    __shared__ uint32_t whist[NW][1 << kMaxLevelBits];
-    __shared__ uint32_t binstart[1 << kMaxLevelBits];
-    __shared__ unsigned long long gclaim[REMOTE ? kMaxPeers : (1 << kMaxLevelBits)];
+    __shared__ uint32_t hist[NB];       // tuples per bin of this tile (block-level shared atomics give the ranks)
+    __shared__ uint32_t binstart[NB];   // exclusive scan of hist
+    __shared__ unsigned long long gclaim[REMOTE ? kMaxPeers : NB];
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
-    __shared__ uint8_t sorted_bin[kScatterTile];
+    __shared__ uint8_t sorted_bin[kKeepBin ? kScatterTile : 1];
     __shared__ uint32_t crc_tab[MODE == 4 ? kCrcSmemWords : 1];
-    const uint32_t wid = threadIdx.x >> 5;
     const uint64_t n = n_ptr ? *n_ptr : n_static;
     const uint32_t b2 = fn.b2;
     const uint32_t P1 = (fn.pmask + 1u) >> b2;
@@ -565,21 +566,21 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
     for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x, it_local++) {
         const int st = it_local % kScatterStages;
         const uint32_t parity = (it_local / kScatterStages) & 1u;
-        for (uint32_t i = threadIdx.x; i < NW * nbins; i += kScatterThreads) whist[i / nbins][i % nbins] = 0u;
+        if (threadIdx.x < NB) hist[threadIdx.x] = 0u;
         mbar_wait(&mbar[st], parity);
         const ScatterItem d = desc[st];
         const uint2* tile = raw + st * kScatterStageTuples + d.skip;
         const uint32_t cnt = d.cnt;
-        __syncthreads();  // whist zeroed
+        __syncthreads();  // hist zeroed, tile landed
         uint2 t[PER];
-        uint32_t rank[PER];  // bin in the high 8 bits, rank within (warp, bin) in the low 24
+        uint32_t rank[PER];  // bin in the high 8 bits, rank within the bin in the low 24
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
                 t[j] = tile[idx];
                 uint32_t bin = bin_of<MODE>(fn, crc_tab, t[j].x);
-                rank[j] = (bin << 24) | atomicAdd(&whist[wid][bin], 1u);
+                rank[j] = (bin << 24) | atomicAdd(&hist[bin], 1u);
             }
         }
         __syncthreads();  // (A) every thread holds its tuples in registers: the stage can be refilled
@@ -587,34 +588,12 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
             uint64_t nxt = item + (uint64_t)kScatterStages * gridDim.x;
             if (nxt < nitems) issue(nxt, st);
         }
-        // per bin: per-warp counts -> per-warp exclusive offsets; claim the bin's output range
-        uint32_t tot = 0;
-        if (threadIdx.x < nbins) {
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                uint32_t c = whist[w][threadIdx.x];
-                whist[w][threadIdx.x] = tot;
-                tot += c;
-            }
-            binstart[threadIdx.x] = tot;
-            if (REMOTE) {
-                unsigned long long c = tot ? atomicAdd_system(peers.cursor[threadIdx.x], (unsigned long long)tot) : 0ull;
-                if (c + tot > peers.capacity) {  // does not fit: flag it and drop the run (the host falls back)
-                    atomicExch(peers.overflow, 1u);
-                    c = ~0ull;
-                }
-                gclaim[threadIdx.x] = c;
-            } else {
-                gclaim[threadIdx.x] = tot ? atomicAdd(&cursor[d.cbase + threadIdx.x], tot) : 0u;
-            }
-        }
-        __syncthreads();  // (B)
-        if (threadIdx.x < 32) {  // exclusive scan over nbins (<=128) totals: 4 per lane
+        if (threadIdx.x < 32) {  // warp 0: exclusive scan over the (<=128) bin counts, 4 per lane
             uint32_t v[4], sum = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 uint32_t bb = threadIdx.x * 4 + q;
-                v[q] = (bb < nbins) ? binstart[bb] : 0u;
+                v[q] = (bb < nbins) ? hist[bb] : 0u;
                 sum += v[q];
             }
             uint32_t inc = sum;
@@ -630,6 +609,19 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
                 if (bb < nbins) binstart[bb] = run;
                 run += v[q];
             }
+        } else if (threadIdx.x - 32u < nbins) {  // meanwhile: one output range per non-empty bin
+            const uint32_t bb = threadIdx.x - 32u;
+            const uint32_t tot = hist[bb];
+            if (REMOTE) {
+                unsigned long long c = tot ? atomicAdd_system(peers.cursor[bb], (unsigned long long)tot) : 0ull;
+                if (c + tot > peers.capacity) {  // does not fit: flag it and drop the run (the host falls back)
+                    atomicExch(peers.overflow, 1u);
+                    c = ~0ull;
+                }
+                gclaim[bb] = c;
+            } else {
+                gclaim[bb] = tot ? atomicAdd(&cursor[d.cbase + bb], tot) : 0u;
+            }
         }
         __syncthreads();  // (C)
 #pragma unroll
@@ -637,23 +629,24 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
                 uint32_t bin = rank[j] >> 24;
-                uint32_t pos = binstart[bin] + whist[wid][bin] + (rank[j] & 0xFFFFFFu);
+                uint32_t pos = binstart[bin] + (rank[j] & 0xFFFFFFu);
                 sorted[pos] = t[j];
-                sorted_bin[pos] = (uint8_t)bin;
+                if (kKeepBin) sorted_bin[pos] = (uint8_t)bin;
             }
         }
         __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
-            uint32_t bin = sorted_bin[i];
+            const uint2 tt = sorted[i];
+            const uint32_t bin = kKeepBin ? (uint32_t)sorted_bin[i] : bin_of<MODE>(fn, crc_tab, tt.x);
             if (REMOTE) {
                 unsigned long long c = gclaim[bin];
-                if (c != ~0ull) peers.buf[bin][c + (i - binstart[bin])] = sorted[i];  // NVLink store (or local)
+                if (c != ~0ull) peers.buf[bin][c + (i - binstart[bin])] = tt;  // NVLink store (or local)
             } else {
-                out[(uint64_t)gclaim[bin] + (i - binstart[bin])] = sorted[i];
+                out[(uint32_t)gclaim[bin] + (i - binstart[bin])] = tt;
             }
         }
-        // next iteration: whist is rewritten before (A'), binstart/gclaim after (A'), sorted after (C'): no
-        // thread can pass (A') before every thread has finished this write-out loop
+        // next iteration: hist is rewritten before its first barrier, binstart/gclaim after (A'), sorted after (C'):
+        // no thread can pass that first barrier before every thread has finished this write-out loop
     }
 }
 
@@ -716,23 +709,29 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
     uint2* tab = reinterpret_cast<uint2*>(smem_raw);                  // kTableCap tuples
     uint32_t* head = reinterpret_cast<uint32_t*>(tab + kTableCap);    // kTableCap heads (index+1, 0 = empty)
     uint16_t* next = reinterpret_cast<uint16_t*>(head + kTableCap);   // kTableCap links
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_item, s_part;
     __shared__ unsigned long long s_red[5][kJoinThreads / 32];
     unsigned long long matches = 0, cpair = 0, crpay = 0, cspay = 0, ckey = 0;
     const uint32_t total = work_off[P];
     const uint64_t pol = policy_evict_first();
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(item_counter, 1u);
+        if (threadIdx.x == 0) {  // one thread fetches the next work item and locates its partition
+            const uint32_t it = atomicAdd(item_counter, 1u);
+            s_item = it;
+            if (it < total) {
+                uint32_t lo = 0, hi = P;
+                while (hi - lo > 1u) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (work_off[mid] <= it) lo = mid; else hi = mid;
+                }
+                s_part = lo;
+            }
+        }
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= total) break;
-        uint32_t lo = 0, hi = P;
-        while (hi - lo > 1u) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (work_off[mid] <= item) lo = mid; else hi = mid;
-        }
-        const uint32_t p = lo;
+        const uint32_t p = s_part;
         const uint32_t chunk = item - work_off[p];
         const uint32_t r0 = r_off[p], nr = r_off[p + 1] - r0;
         const uint32_t sbeg = s_off[p] + chunk * kSChunk;

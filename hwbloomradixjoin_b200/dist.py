@@ -259,7 +259,11 @@ class PeerFabric:
     NVLink: no send buffers, no counts on the host, no collective for the data. Ranks are separated by tiny
     stream-ordered all-reduces (route -> consume)."""
 
-    CTRL_BYTES = 256  # [0] R cursor u64, [1] S cursor u64, [2] overflow u32, rest reserved
+    # two sets of control words {R cursor u64, S cursor u64, overflow u32, pad}: join i uses set i%2 and zeroes the other
+    # one, which no peer touches before join i+1 -- and every rank enters join i+1 only after the barriers of join i,
+    # i.e. after this rank's zeroing (stream order). So no extra "cursors are zero" barrier is needed.
+    CTRL_BYTES = 256
+    SET_BYTES = 32
 
     def __init__(self, ops: "CudaOps", cap_r: int, cap_s: int, group=None):
         self.ops, self.group = ops, group
@@ -295,6 +299,8 @@ class PeerFabric:
             self.peer.append(ptrs)
         self._bar = torch.zeros(1, dtype=torch.int32, device=ops.device)
         self.ctrl_view = ops.view_int64(self.local[2], self.CTRL_BYTES // 8)
+        self.parity = 0
+        self.ctrl_view.zero_()
         self.barrier()
 
     def barrier(self):
@@ -307,9 +313,13 @@ class PeerFabric:
             arr[g] = self.peer[g][which] + byte_offset
         return arr
 
-    def reset(self):
-        self.ctrl_view.zero_()
-        self.barrier()  # nobody routes into a rank that has not zeroed its cursors yet
+    def begin_join(self) -> int:
+        """switch to the other set of control words and zero the one the NEXT join will use; returns the byte offset
+        of the active set"""
+        self.parity ^= 1
+        nxt = (self.parity ^ 1) * (self.SET_BYTES // 8)
+        self.ctrl_view[nxt:nxt + self.SET_BYTES // 8].zero_()
+        return self.parity * self.SET_BYTES
 
     def close(self):
         L = self.ops.L
@@ -342,13 +352,12 @@ def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Ssh
     cargs = slice_args.to_c() if slice_args is not None else None
     cref = C.byref(cargs) if cargs is not None else None
     tm = PhaseTimer(time_phases)
-    ctrl = fabric.local[2]
     tm.mark("start")
-    fabric.reset()
-    tm.mark("reset_barrier")
+    coff = fabric.begin_join()
+    ctrl = fabric.local[2] + coff
     # (1) R: fused partition + all-to-all
     h = ops._wrap(Rshard)
-    rc = L.hwbrj_route_peer(h, world, cref, fabric.ptr_array(0), fabric.ptr_array(2, 0), fabric.cap_r, ctrl + 16)
+    rc = L.hwbrj_route_peer(h, world, cref, fabric.ptr_array(0), fabric.ptr_array(2, coff), fabric.cap_r, ctrl + 16)
     L.hwbrj_rel_free(h)
     if rc != 0:
         raise RuntimeError("hwbrj_route_peer(R) failed")
@@ -376,7 +385,7 @@ def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Ssh
         cnt = None
         hsurv = ops._wrap(Sshard)
     # (4) survivors: fused partition + all-to-all
-    rc = L.hwbrj_route_peer(hsurv, world, cref, fabric.ptr_array(1), fabric.ptr_array(2, 8), fabric.cap_s, ctrl + 16)
+    rc = L.hwbrj_route_peer(hsurv, world, cref, fabric.ptr_array(1), fabric.ptr_array(2, coff + 8), fabric.cap_s, ctrl + 16)
     L.hwbrj_rel_free(hsurv)
     if rc != 0:
         raise RuntimeError("hwbrj_route_peer(S) failed")
@@ -391,7 +400,7 @@ def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Ssh
     if rc != 0:
         raise RuntimeError("hwbrj_join_device failed")
     tm.mark("local_join")
-    c = fabric.ctrl_view.tolist()
+    c = fabric.ctrl_view[coff // 8:coff // 8 + 4].tolist()
     filtered_local = int(cnt.item()) if cnt is not None else 0
     overflow = c[2] & 0xFFFFFFFF
     vals = _reduce_scalars([st.matches, filtered_local, st.checksum_pair, st.checksum_rpay, st.checksum_spay,
