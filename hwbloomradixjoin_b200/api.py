@@ -144,6 +144,14 @@ def run(algo: str, relR, relS, nthreads: int = 2, bloom: BloomFilterArgs | None 
     return withbloom(relR, relS, nthreads, bloom) if bloom is not None else plain(relR, relS, nthreads)
 
 
+def last_filter(m: int) -> np.ndarray:
+    """bitmap (m/8 bytes) of the filter the most recent Bloom join built on the device"""
+    out = np.empty(m // 8, dtype=np.uint8)
+    if N.load().hwbrj_last_filter(out.ctypes.data_as(C.c_void_p), out.shape[0]) != 0:
+        raise RuntimeError("no filter of that size")
+    return out
+
+
 def set_quiet(quiet: bool = True) -> None:
     N.load().hwbrj_set_quiet(int(quiet))
 
@@ -154,6 +162,11 @@ def set_radix_bits(bits: int) -> None:
 
 def set_range_passes(passes: int) -> None:
     N.load().hwbrj_set_range_passes(int(passes))
+
+
+def set_hash_partition(mode: int) -> None:
+    """0 never, 1 automatic (filters > 32 MiB), 2 whenever possible"""
+    N.load().hwbrj_set_hash_partition(int(mode))
 
 
 def device_count() -> int:

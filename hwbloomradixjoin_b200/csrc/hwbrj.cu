@@ -83,6 +83,8 @@ struct Ctx {
     DevBuf cur1b, cur2b, tilesb;          // second set of scatter cursors: R partitioning may overlap the S probe
     cudaStream_t side_stream = nullptr;   // R partitioning runs here while K2 runs on the main stream
     cudaEvent_t ev_side[4];
+    bool hash_partition = true;           // BASIC k<=1: partition on the filter-slice index, build the filter in smem
+    bool hash_partition_force = false;    // HWBRJ_HASH_PARTITION=2: also for small filters (tests)
     bool overlap_r_partition = false;     // measured: the scatter traffic evicts the probed filter range (C1: 11.1 vs 9.9 ms)
     hwbrj_stats_t last;
     bool quiet = false;
@@ -121,7 +123,8 @@ static void init_ctx() {
     const int hist_smem = ((1 << kMaxRadixBits) + kCrcSmemWords) * 4;
     CK(cudaFuncSetAttribute(k_build_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    CK(cudaFuncSetAttribute(k_join, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
+    CK(cudaFuncSetAttribute(k_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
+    CK(cudaFuncSetAttribute(k_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
     if (const char* s = getenv("HWBRJ_RADIX_BITS")) g.radix_bits_override = atoi(s);
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
@@ -131,9 +134,16 @@ static void init_ctx() {
     CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    CK(cudaFuncSetAttribute(k_scatter<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
+    CK(cudaFuncSetAttribute(k_filter_from_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_build_hist<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    if (const char* s = getenv("HWBRJ_HASH_PARTITION")) {
+        g.hash_partition = atoi(s) != 0;
+        g.hash_partition_force = atoi(s) == 2;
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter1, k_scatter<1>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter2, k_scatter<2>, kScatterThreads, kScatterSmem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join, kJoinThreads, kTableCap * (8 + 4 + 2)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join<false>, kJoinThreads, kTableCap * (8 + 4 + 2)));
     g.occ_scatter1 = std::max(g.occ_scatter1, 1);
     g.occ_scatter2 = std::max(g.occ_scatter2, 1);
     g.occ_join = std::max(g.occ_join, 1);
@@ -278,9 +288,17 @@ struct Partitioned {
 };
 
 // histogram already in `hist`; runs scan + 1 or 2 scatter passes. n_dev (optional) = device-side tuple count.
+// Partition function of the join: key & (2^bits-1) (the reference's radix clustering), or -- for a BASIC k<=1 filter
+// -- the filter-slice index (crapwow(42,key) & (m-1)) >> (log2 m - bits), which lets K1' build the filter in shared memory.
+struct PartFn {
+    bool hash = false;
+    uint32_t seed = 42u, size_mask = 0u;
+    int log2m = 0;
+};
+
 static const uint2* run_partition(const uint2* in, uint64_t n, const unsigned long long* n_dev, int bits, int b2,
                                   uint32_t* hist, uint32_t* off, uint2* t1, uint2* t2, int& launches,
-                                  cudaStream_t stream = nullptr, bool second_set = false) {
+                                  cudaStream_t stream = nullptr, bool second_set = false, PartFn pf = PartFn()) {
     if (!stream) stream = g.stream;
     uint32_t* cur1 = second_set ? g.cur1b.as<uint32_t>() : g.cur1.as<uint32_t>();
     uint32_t* cur2 = second_set ? g.cur2b.as<uint32_t>() : g.cur2.as<uint32_t>();
@@ -295,6 +313,22 @@ static const uint2* run_partition(const uint2* in, uint64_t n, const unsigned lo
     fn.pmask = pmask;
     fn.b2 = (uint32_t)b2;
     fn.submask = (1u << b2) - 1u;
+    if (pf.hash) {
+        fn.seed = pf.seed;
+        fn.size_mask = pf.size_mask;
+        fn.oshift = (uint32_t)(pf.log2m - b1);  // level 1: the top b1 bits of the slice index
+        fn.binmask = 0xFFFFFFFFu;
+        k_scatter<3><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, stream>>>(
+            in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off, tiles, cur1, fn, g.d_crc, 1u << b1);
+        launches++;
+        if (b2 == 0) return t1;
+        fn.oshift = (uint32_t)(pf.log2m - bits);  // level 2: the low b2 bits of the slice index
+        fn.binmask = (1u << b2) - 1u;
+        k_scatter<5><<<g.sms * g.occ_scatter2, kScatterThreads, kScatterSmem, stream>>>(t1, t2, nullptr, n, off, tiles,
+                                                                                       cur2, fn, g.d_crc, 1u << b2);
+        launches++;
+        return t2;
+    }
     k_scatter<1><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, stream>>>(
         in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off, tiles, cur1, fn, g.d_crc, 1u << b1);
     launches++;
@@ -356,15 +390,34 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     int nranges = 1;
     const int hist_smem = (int)((P + kCrcSmemWords) * 4);
     const int grid_hist = g.sms * 2;
+    // Hash-partitioned variant (BASIC, k <= 1): the join partitions on the filter-slice index, so each partition owns a
+    // contiguous m/P-bit slice of the filter and K1' builds it in shared memory -- no global atomics, R read once less.
+    PartFn pf;
+    // Used when the filter is too big for its atomics to stay L2-resident (> 32 MiB: K1 1.25 -> 0.68 ms at C1); for
+    // small filters the plain atomics are faster (C0: 1.71 vs 1.80 ms) and the radix table index has shorter chains.
+    if (args && g.hash_partition && args->variant == BASIC && args->k <= 1 && bits >= 1 &&
+        (args->m / 8 > (32ull << 20) || g.hash_partition_force) && ilog2_u64(args->m) >= bits + 5 &&
+        (args->m >> bits) / 8 <= 96 * 1024 && !g.overlap_r_partition) {
+        pf.hash = true;
+        pf.size_mask = (uint32_t)(args->m - 1);
+        pf.log2m = ilog2_u64(args->m);
+    }
+    const uint32_t hshift = pf.hash ? (uint32_t)(pf.log2m - bits) : 0u;
     if (args) {
         bp = make_bloom(args, 42u, g.filter.as<uint32_t>());  // seed 42: parallel_radix_join_bloom.c:1583,1823
         nranges = pick_ranges(args);
         bp.nranges = (uint32_t)nranges;
         bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-        for (int r = 0; r < nranges; r++) {
-            bp.range_id = (uint32_t)r;
-            k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+        if (pf.hash) {
+            k_build_hist<false, true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc,
+                                                                               g.histR.as<uint32_t>(), pmask, hshift);
             launches++;
+        } else {
+            for (int r = 0; r < nranges; r++) {
+                bp.range_id = (uint32_t)r;
+                k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
+                launches++;
+            }
         }
     } else {
         k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
@@ -382,7 +435,14 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         CK(cudaEventRecord(g.ev_side[1], g.side_stream));
     } else {
         Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(), g.rt1.as<uint2>(),
-                           g.rp.as<uint2>(), launches);
+                           g.rp.as<uint2>(), launches, nullptr, false, pf);
+    }
+    CK(cudaEventRecord(g.ev_side[2], g.stream));
+    if (pf.hash && args->k >= 1) {  // K1': the filter, slice by slice, from the partitioned R (k = 0 sets no bit)
+        const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
+        k_filter_from_parts<<<g.sms * 4, 256, slice_words * 4, g.stream>>>(Rp, g.offR.as<uint32_t>(), P, g.filter.as<uint32_t>(),
+                                                                          slice_words, 42u, pf.size_mask);
+        launches++;
     }
     CK(cudaEventRecord(g.ev[3], g.stream));
     const uint2* Sin = dS;
@@ -395,19 +455,28 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         n_dev = &ctrl->survivors;
     }
     // radix histogram of the tuples that go on to the join (survivors, or all of S without a filter)
-    k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
+    if (pf.hash)
+        k_build_hist<false, true><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc,
+                                                                           g.histS.as<uint32_t>(), pmask, hshift);
+    else
+        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
     launches++;
     CK(cudaEventRecord(g.ev[4], g.stream));
     // with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc
     const uint2* Sp = run_partition(Sin, nS, n_dev, bits, b2, g.histS.as<uint32_t>(), g.offS.as<uint32_t>(),
-                                    g.st1.as<uint2>(), g.sc.as<uint2>(), launches);
+                                    g.st1.as<uint2>(), g.sc.as<uint2>(), launches, nullptr, false, pf);
     CK(cudaEventRecord(g.ev[5], g.stream));
     if (overlap) CK(cudaStreamWaitEvent(g.stream, g.ev_side[1], 0));
     k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>());
     launches++;
-    k_join<<<g.sms * g.occ_join, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
-        Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
-        &ctrl->item_counter, &ctrl->acc);
+    if (pf.hash)
+        k_join<true><<<g.sms * g.occ_join, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
+            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
+            &ctrl->item_counter, &ctrl->acc);
+    else
+        k_join<false><<<g.sms * g.occ_join, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
+            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
+            &ctrl->item_counter, &ctrl->acc);
     launches++;
     CK(cudaEventRecord(g.ev[6], g.stream));
     Control h;
@@ -430,6 +499,12 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     st.ms_total = ms(1, 6);
     st.ms_build = ms(1, 2);
     st.ms_part_r = ms(2, 3);
+    if (pf.hash) {  // the filter is built after the scatter passes: book it under "build"
+        float f = 0;
+        CK(cudaEventElapsedTime(&f, g.ev_side[2], g.ev[3]));
+        st.ms_build += f;
+        st.ms_part_r -= f;
+    }
     if (overlap) CK(cudaEventElapsedTime(&st.ms_part_r, g.ev_side[0], g.ev_side[1]));  // overlapped with ms_probe
     st.ms_probe = ms(3, 4);
     st.ms_part_s = ms(4, 5);
@@ -540,10 +615,21 @@ int hwbrj_last_stats(hwbrj_stats_t* out) {
     return 0;
 }
 int64_t hwbrj_last_filtered(void) { return g.last.filtered; }
+int hwbrj_last_filter(unsigned char* bitmap_out, uint64_t nbytes) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!bitmap_out || nbytes > g.filter.cap) return -1;
+    CK(cudaMemcpy(bitmap_out, g.filter.p, nbytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
 uint64_t hwbrj_last_checksum(void) { return g.last.checksum_pair; }
 void hwbrj_set_quiet(int quiet) { g.quiet = quiet != 0; }
 void hwbrj_set_radix_bits(int bits) { g.radix_bits_override = bits; }
 void hwbrj_set_range_passes(int passes) { g.range_passes_override = passes; }
+void hwbrj_set_hash_partition(int mode) {
+    g.hash_partition = mode != 0;
+    g.hash_partition_force = mode == 2;
+}
 const char* hwbrj_version(void) { return "hwbrj-b200 0.1 (sm_100a)"; }
 int hwbrj_device_count(void) {
     int n = 0;
@@ -791,6 +877,7 @@ static BinFn owner_fn(int world, const bloom_filter_args_t* slice_args, int& mod
     memset(&fn, 0, sizeof(fn));
     const int gbits = ilog2_u64((uint64_t)world);
     fn.seed = 42u;
+    fn.binmask = 0xFFFFFFFFu;
     if (slice_args && slice_args->variant == BLOCKED) {
         mode = 4;  // owner = top bits of the block index (all k bits of a key live in that block)
         uint64_t nblocks = slice_args->m / slice_args->B;

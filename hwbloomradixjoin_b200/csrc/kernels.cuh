@@ -174,11 +174,12 @@ __global__ void k_hash_many(int which, uint32_t seed, const int32_t* __restrict_
 // replaces the build branch of the histogram loop, parallel_radix_join_bloom.c:794-805 + add_generic
 // (bloom_filter.c:74-89). Also used without a filter (plain PRO histogram, parallel_radix_join.c:770-775).
 // dynamic smem: hist[pmask+1] then crc table[kCrcSmemWords]
-template <bool BLOOM>
+// HASHPID: the partition id is the filter-slice index (crapwow(seed,key) & size_mask) >> hshift instead of key & pmask
+template <bool BLOOM, bool HASHPID = false>
 __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ rel, uint64_t n_static,
                                                     const unsigned long long* __restrict__ n_ptr, BloomParams bp,
                                                     const uint32_t* __restrict__ g_crc, uint32_t* __restrict__ ghist,
-                                                    uint32_t pmask) {
+                                                    uint32_t pmask, uint32_t hshift = 0) {
     extern __shared__ uint32_t smem[];
     const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
     uint32_t* hist = smem;
@@ -197,12 +198,24 @@ __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ r
             if (!bloom_in_range(bp, base + h)) return;
             bloom_insert(bp, base, h, y);
         }
-        atomicAdd(&hist[key & pmask], 1u);
+        if (HASHPID) atomicAdd(&hist[(hash_crapwow(bp.seed, key) & bp.size_mask) >> hshift], 1u);
+        else atomicAdd(&hist[key & pmask], 1u);
     };
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
-        uint4 v = ld_stream_v4(rel4 + i, pol);
-        one(v.x);
-        one(v.z);
+    constexpr int U = 4;  // 128-bit loads in flight per thread
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t idx = i + (uint64_t)u * stride;
+            v[u] = idx < npairs ? ld_stream_v4(rel4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (i + (uint64_t)u * stride < npairs) {
+                one(v[u].x);
+                one(v[u].z);
+            }
+        }
     }
     if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) one(rel[n - 1].x);
     __syncthreads();
@@ -419,17 +432,20 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist
 
 // ---- destination-bin functions of the scatter kernel -----------------------------------------------------------------
 // MODE 1: radix level 1 (pid >> b2)      MODE 2: radix level 2 (pid & (2^b2-1))
-// MODE 3: owner GPU by hash slice, BASIC filter / plain join: (crapwow(seed,key) & size_mask) >> oshift
+// MODE 3: hash bins ((crapwow(seed,key) & size_mask) >> oshift) & binmask -- owner GPU by filter slice, and level 1
+//         of the hash-partitioned join (partition = filter slice, so the filter can be built in shared memory)
 // MODE 4: owner GPU by hash slice, BLOCKED filter: (crc32c(seed,key) & nblocks_mask) >> oshift
+// MODE 5: MODE 3's bin function on the level-2 tile schedule (input = level-1 output)
 struct BinFn {
     uint32_t pmask, b2, submask;            // radix modes
-    uint32_t seed, size_mask, oshift;       // owner modes
+    uint32_t seed, size_mask, oshift;       // hash modes
+    uint32_t binmask;                       // hash modes: mask applied after the shift (level 2), else ~0
 };
 template <int MODE>
 __device__ __forceinline__ uint32_t bin_of(const BinFn& f, const uint32_t* crc_tab, uint32_t key) {
     if (MODE == 1) return (key & f.pmask) >> f.b2;
     if (MODE == 2) return key & f.submask;
-    if (MODE == 3) return (hash_crapwow(f.seed, key) & f.size_mask) >> f.oshift;
+    if (MODE == 3 || MODE == 5) return ((hash_crapwow(f.seed, key) & f.size_mask) >> f.oshift) & f.binmask;
     return (crc32c_tab(crc_tab, f.seed, key) & f.size_mask) >> f.oshift;
 }
 
@@ -488,7 +504,7 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
                                                     const uint32_t* __restrict__ tile_off, uint32_t P1, uint32_t b2) {
     ScatterItem it;
     uint64_t src0;
-    if (MODE != 2) {
+    if (MODE != 2 && MODE != 5) {
         src0 = item * kScatterTile;
         it.cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
         it.cbase = 0u;
@@ -544,7 +560,7 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
     const uint64_t n = n_ptr ? *n_ptr : n_static;
     const uint32_t b2 = fn.b2;
     const uint32_t P1 = (fn.pmask + 1u) >> b2;
-    const uint64_t nitems = (MODE != 2) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
+    const uint64_t nitems = (MODE != 2 && MODE != 5) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
     if (MODE == 4) load_crc_tab(crc_tab, g_crc);
     if (threadIdx.x == 0) {
         for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
@@ -650,6 +666,31 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
     }
 }
 
+// ---- K1': Bloom filter built from hash partitions, in shared memory, without global atomics ------------------------
+// When the join partitions on the filter-slice index (partition p = keys whose bit lies in bits [p*S, (p+1)*S) of the
+// filter, S = m / 2^bits), every partition owns one contiguous slice: a CTA zeroes the slice in shared memory, ORs in
+// the bits of its partition's keys with shared-memory atomics and writes the slice out with coalesced stores. This
+// replaces add_generic's atomic OR per key (bloom_filter.c:74-89) for BASIC k = 1; the bitmap is byte-identical.
+__global__ void __launch_bounds__(256) k_filter_from_parts(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
+                                                          uint32_t P, uint32_t* __restrict__ filter, uint32_t slice_words,
+                                                          uint32_t seed, uint32_t size_mask) {
+    extern __shared__ uint32_t s_slice[];
+    const uint32_t slice_mask = slice_words * 32u - 1u;
+    for (uint32_t p = blockIdx.x; p < P; p += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) s_slice[i] = 0u;
+        __syncthreads();
+        const uint32_t lo = r_off[p], hi = r_off[p + 1];
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint32_t h = hash_crapwow(seed, Rp[i].x) & size_mask & slice_mask;
+            atomicOr(&s_slice[h >> 5], 1u << (h & 31u));
+        }
+        __syncthreads();
+        uint32_t* dst = filter + (uint64_t)p * slice_words;
+        for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) dst[i] = s_slice[i];
+        __syncthreads();
+    }
+}
+
 // ---- join work list: one item per (partition, S chunk) --------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_worklist(const uint32_t* __restrict__ r_off, const uint32_t* __restrict__ s_off,
                                                   uint32_t P, uint32_t* __restrict__ work_off) {
@@ -701,6 +742,8 @@ __global__ void __launch_bounds__(1024) k_worklist(const uint32_t* __restrict__ 
 // memory, idx = (key >> radix_bits) & (N-1) (HASH_BIT_MODULO with MASK=(N-1)<<bits), every equal key along the
 // chain counts. R partitions larger than kTableCap are processed in rounds; S partitions larger than kSChunk are
 // split over several work items (each rebuilds the table) so that skewed S does not serialise on one SM.
+// HASHPART: partitions come from the hash (filter-slice) partitioning, so the table index is key & (N-1).
+template <bool HASHPART>
 __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
                                                       const uint2* __restrict__ Sp, const uint32_t* __restrict__ s_off,
                                                       const uint32_t* __restrict__ work_off, uint32_t P, uint32_t bits,
@@ -758,7 +801,7 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
                     uint32_t i = i0 + u * kJoinThreads;
                     if (i < cnt) {
                         tab[i] = t[u];
-                        next[i] = (uint16_t)atomicExch(&head[(t[u].x >> bits) & nmask], i + 1u);
+                        next[i] = (uint16_t)atomicExch(&head[(HASHPART ? t[u].x : (t[u].x >> bits)) & nmask], i + 1u);
                     }
                 }
             }
@@ -775,7 +818,7 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
                     uint32_t i = i0 + u * kJoinThreads;
                     if (i < send) {
                         const uint2 s = sv[u];
-                        for (uint32_t hit = head[(s.x >> bits) & nmask]; hit; hit = next[hit - 1u]) {
+                        for (uint32_t hit = head[(HASHPART ? s.x : (s.x >> bits)) & nmask]; hit; hit = next[hit - 1u]) {
                             uint2 r = tab[hit - 1u];
                             if (r.x == s.x) {
                                 matches++;

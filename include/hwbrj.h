@@ -135,11 +135,16 @@ typedef struct hwbrj_stats_t {
 int      hwbrj_last_stats(hwbrj_stats_t * out);
 int64_t  hwbrj_last_filtered(void);
 uint64_t hwbrj_last_checksum(void); /* checksum_pair */
+/* the Bloom filter bitmap the most recent Bloom join built on the device (first nbytes = m/8) */
+int      hwbrj_last_filter(unsigned char * bitmap_out, uint64_t nbytes);
 
 void hwbrj_set_quiet(int quiet);    /* 1: suppress the reference-style stdout lines */
 /* tuning knobs (also read from env HWBRJ_RADIX_BITS / HWBRJ_RANGE_PASSES); 0 = automatic */
 void hwbrj_set_radix_bits(int bits);
 void hwbrj_set_range_passes(int passes);
+/* partition the join on the filter-slice index and build the filter in shared memory (BASIC k<=1):
+ * 0 never, 1 when the filter exceeds 32 MiB (default), 2 whenever the slices fit */
+void hwbrj_set_hash_partition(int mode);
 const char * hwbrj_version(void);
 int  hwbrj_device_count(void);
 

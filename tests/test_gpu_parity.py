@@ -157,6 +157,27 @@ def test_bpro_vs_oracle(Hgpu, oracle_mod, case):
     assert (R == Rc).all() and (S == Sc).all()  # unlike the reference the inputs are left untouched
 
 
+@pytest.mark.parametrize("m,k", [(1 << 21, 1), (1 << 24, 1), (1 << 16, 1), (1 << 21, 0)])
+def test_filter_built_inside_the_join_is_byte_identical(Hgpu, oracle_mod, m, k):
+    """BASIC k<=1 joins partition on the filter-slice index and build the filter in shared memory (K1'); the
+    resulting bitmap must still be the reference's, byte for byte, whatever the radix fan-out."""
+    R, S = inputs(oracle_mod, 250_000, 2_000_000, 0.01)
+    exp = oracle_mod.bloom_build(R, 0, m, k, 512)
+    for bits in (0, 4, 9, 13):
+        Hgpu.set_radix_bits(bits)
+        Hgpu.set_hash_partition(2)  # force the shared-memory build also for these small filters
+        try:
+            res = Hgpu.BPRO(R, S, 1, Hgpu.BloomFilterArgs(0, m, k, 512))
+            assert Hgpu.last_filter(m).tobytes() == exp.tobytes(), (m, k, bits)
+            assert scalars(res) == oscalars(oracle_mod.join(R, S, True, 0, m, k, 512))
+            Hgpu.set_hash_partition(0)  # and the atomic build of the radix-partitioned path
+            res = Hgpu.BPRO(R, S, 1, Hgpu.BloomFilterArgs(0, m, k, 512))
+            assert Hgpu.last_filter(m).tobytes() == exp.tobytes(), (m, k, bits)
+        finally:
+            Hgpu.set_radix_bits(0)
+            Hgpu.set_hash_partition(1)
+
+
 @pytest.mark.parametrize("q", [0.001, 0.1, 0.5, 1.0])
 def test_selectivity_sweep(Hgpu, oracle_mod, q):
     R, S = inputs(oracle_mod, 250_000, 2_000_000, q)
