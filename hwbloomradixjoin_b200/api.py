@@ -225,6 +225,16 @@ def join_device(R: DeviceRelation, S: DeviceRelation, bloom: BloomFilterArgs | N
                       st.checksum_key, st.as_dict())
 
 
+def fpr_count(R: DeviceRelation, S: DeviceRelation, bloom: BloomFilterArgs, seed: int) -> int:
+    """test_bloom_fpr (unit_tests.c:191-241) on the device: filter built with `seed` from R, number of S keys passing"""
+    bloom.check()
+    cargs = bloom.to_c()
+    n = N.load().hwbrj_fpr_count(R._h, S._h, C.byref(cargs), seed & 0xFFFFFFFF)
+    if n < 0:
+        raise RuntimeError("hwbrj_fpr_count failed")
+    return int(n)
+
+
 # ---- building blocks (parity tests) --------------------------------------------------------------------------
 def hash_many(which: int, seed: int, keys) -> np.ndarray:
     keys = np.ascontiguousarray(keys, dtype=np.int32)

@@ -840,6 +840,39 @@ int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_
     return (int64_t)cnt;
 }
 
+// device analogue of the reference's FPR measurement (test_bloom_fpr, unit_tests.c:191-241): build a filter with the
+// given seed from R, probe S, return how many S keys pass
+int64_t hwbrj_fpr_count(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, uint32_t seed) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!R || !S || !args || check_args_impl(args, true)) return -1;
+    g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
+    g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
+    g.sc.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    g.st1.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    g.ctrl.ensure(sizeof(Control));
+    CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
+    CK(cudaMemsetAsync(g.histR.p, 0, 4, g.stream));
+    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
+    Control* ctrl = g.ctrl.as<Control>();
+    BloomParams bp = make_bloom(args, seed, g.filter.as<uint32_t>());
+    int nranges = pick_ranges(args);
+    bp.nranges = (uint32_t)nranges;
+    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    for (int r = 0; r < nranges; r++) {
+        bp.range_id = (uint32_t)r;
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, R->n_dev, bp, g.d_crc,
+                                                                                  g.histR.as<uint32_t>(), 0u);
+    }
+    if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    run_probe(S->d, S->n, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(), nranges > 2 ? g.d1.as<uint2>() : nullptr);
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    return (int64_t)cnt;
+}
+
 int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out, uint64_t* offsets) {
     std::lock_guard<std::mutex> lock(g.mu);
     init_ctx();

@@ -182,6 +182,9 @@ int hwbrj_bloom_build(const tuple_t * R, uint64_t nR, const bloom_filter_args_t 
  * (any order) and their number (bloom_filter.c:93-111,135-141) */
 int64_t hwbrj_bloom_probe(const unsigned char * bitmap, const tuple_t * S, uint64_t nS,
                           const bloom_filter_args_t * args, uint32_t seed, tuple_t * survivors_out);
+/* device analogue of the reference's FPR measurement (test_bloom_fpr, unit_tests.c:191-241): build a filter with
+ * `seed` from the device-resident R, probe the device-resident S, return the number of passing S keys */
+int64_t hwbrj_fpr_count(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args, uint32_t seed);
 /* radix-partition a relation on the GPU with the pipeline's own kernels: out receives the tuples
  * grouped by (key & (2^bits-1)) in increasing partition order, offsets (2^bits+1 entries) the
  * partition boundaries (parallel_radix_join_bloom.c:574-608,759-852 equivalent) */

@@ -75,6 +75,9 @@ def lib():
         L.orc_gen_relation.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_double,
                                        C.c_uint64]
         L.orc_gen_zipf.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_uint]
+        L.orc_glibc_rand.argtypes = [C.c_uint, C.c_void_p, C.c_uint32]
+        L.orc_fpr_samples.restype = C.c_uint32
+        L.orc_fpr_samples.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -161,6 +164,14 @@ def gen_zipf(s: int, r: int, theta: float, seed: int = 54321) -> np.ndarray:
     rel = np.empty(s, dtype=TUPLE)
     lib().orc_gen_zipf(_tp(rel), s, r, theta, seed)
     return rel
+
+
+def fpr_samples(seed: int, n_samples: int, n_insertions: int):
+    """inputs of `unittests 2 seed n_samples n_insertions m k_max` (unit_tests.c:243-297) and the filter seed"""
+    R = np.empty(n_insertions, dtype=TUPLE)
+    S = np.empty(n_samples, dtype=TUPLE)
+    fseed = lib().orc_fpr_samples(seed, n_samples, n_insertions, _tp(R), _tp(S))
+    return R, S, fseed
 
 
 # ----------------------------------------------------------------------------------------------

@@ -547,3 +547,89 @@ orc_gen_zipf(orc_tuple_t * rel, uint64_t stream_size, uint32_t alphabet_size, do
     free(alphabet);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* inputs of the reference's Bloom FPR measurement (`unittests 2 ...`)                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* glibc rand()/srand() restated (TYPE_3 additive feedback generator, x^31 + x^3 + 1): the reference draws ~2.1e9
+ * numbers for one FPR run and libc's rand() takes a lock per call (~27 ns -> a minute); this lock-free copy of the
+ * same recurrence is ~10x faster. tests/test_oracle.py checks it against libc's rand() itself. */
+typedef struct {
+    int32_t r[34];
+    int     f, b; /* front / rear indices into r[3..33] style ring (implemented as a 31-entry ring) */
+    int32_t ring[31];
+} grand_t;
+
+static void
+grand_seed(grand_t * g, unsigned int seed)
+{
+    int32_t r[344 + 31];
+    if (seed == 0) seed = 1;
+    r[0] = (int32_t) seed;
+    for (int i = 1; i < 31; i++) {
+        int64_t hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        int64_t w  = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = (int32_t) w;
+    }
+    for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+    for (int i = 34; i < 344; i++) r[i] = (int32_t) ((uint32_t) r[i - 31] + (uint32_t) r[i - 3]);
+    /* keep the last 31 values as the ring; next output index is 344 */
+    for (int i = 0; i < 31; i++) g->ring[i] = r[344 - 31 + i];
+    g->f = 0; /* position of r[i-31] */
+}
+
+static inline int
+grand_next(grand_t * g)
+{
+    /* r[i] = r[i-31] + r[i-3]; ring[f] holds r[i-31], ring[(f+28)%31] holds r[i-3] */
+    int      b = g->f + 28;
+    if (b >= 31) b -= 31;
+    uint32_t v = (uint32_t) g->ring[g->f] + (uint32_t) g->ring[b];
+    g->ring[g->f] = (int32_t) v;
+    if (++g->f == 31) g->f = 0;
+    return (int) (v >> 1);
+}
+
+/** first n outputs of the restated generator (for the test against libc) */
+void
+orc_glibc_rand(unsigned int seed, int * out, uint32_t n)
+{
+    grand_t g;
+    grand_seed(&g, seed);
+    for (uint32_t i = 0; i < n; i++) out[i] = grand_next(&g);
+}
+
+/* random_unique_gen_range (unit_tests.c:155-173): selection sampling (Knuth) of n sorted unique values from
+ * [min, min + (max-min)) with rand(); key = payload = value. */
+static void
+unique_range(grand_t * g, orc_tuple_t * arr, uint64_t n, int32_t min, int32_t max)
+{
+    uint32_t inserted  = 0;
+    int32_t  m_options = max - min;
+    for (uint32_t i = 0; i < (uint32_t) m_options && inserted < n; ++i) {
+        int rn = (int) (n - inserted);
+        int rm = m_options - (int) i;
+        if (grand_next(g) % rm < rn) {
+            arr[inserted].key     = min + (int32_t) i;
+            arr[inserted].payload = min + (int32_t) i;
+            inserted++;
+        }
+    }
+}
+
+/** test_bloom_fpr_wrapper (unit_tests.c:243-297): srand(seed+1); R = n_insertions values below
+ *  threshold = INT32_MAX * n_ins/(n_ins+n_samples), S = n_samples values above it; every filter of the table is
+ *  then created with the seed `srand(seed); rand()` (test_bloom_fpr, unit_tests.c:195-201). Returns that seed. */
+uint32_t
+orc_fpr_samples(int seed, uint32_t n_samples, uint32_t n_insertions, orc_tuple_t * R, orc_tuple_t * S)
+{
+    grand_t g;
+    grand_seed(&g, (unsigned) (seed + 1));
+    int32_t threshold = (int32_t) (2147483647 * (n_insertions / (double) (n_insertions + n_samples)));
+    unique_range(&g, R, n_insertions, 0, threshold);
+    unique_range(&g, S, n_samples, threshold + 1, 2147483647);
+    grand_seed(&g, (unsigned) seed);
+    return (uint32_t) grand_next(&g);
+}

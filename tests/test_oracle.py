@@ -183,3 +183,14 @@ def test_reference_generator_multiset(oracle_mod):
     S = oracle_mod.ref_generate(1, s, r, q=q, seed=54321, nthreads=4)
     assert (np.sort(R["key"]) == np.sort(oracle_mod.gen_R(r, nthreads=4)["key"])).all()
     assert (np.sort(S["key"]) == np.sort(oracle_mod.gen_S(s, r, q, nthreads=4)["key"])).all()
+
+
+def test_glibc_rand_restatement(oracle_mod):
+    """the lock-free copy of glibc's rand() used for the FPR samples is checked against libc itself"""
+    import ctypes as C
+    libc = C.CDLL(None)
+    for seed in (817263, 817264, 1, 0, 54321):
+        out = np.empty(5000, dtype=np.int32)
+        oracle_mod.lib().orc_glibc_rand(seed, out.ctypes.data_as(C.c_void_p), out.shape[0])
+        libc.srand(seed)
+        assert out.tolist() == [libc.rand() for _ in range(out.shape[0])]
