@@ -49,7 +49,7 @@ EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_la
            "hwbrj_last_checksum", "hwbrj_last_filter", "hwbrj_set_quiet", "hwbrj_set_radix_bits", "hwbrj_set_range_passes", "hwbrj_set_hash_partition", "hwbrj_version",
            "hwbrj_device_count", "hwbrj_check_args", "hwbrj_rel_upload", "hwbrj_rel_generate", "hwbrj_rel_download",
            "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_host_alloc", "hwbrj_host_free",
-           "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_fpr_count", "hwbrj_radix_partition",
+           "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_fpr_count", "hwbrj_materialize_last", "hwbrj_materialize_last_device", "hwbrj_radix_partition",
            "hwbrj_set_stream", "hwbrj_reset_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
            "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe",
            "hwbrj_rel_wrap_counted", "hwbrj_symm_alloc", "hwbrj_symm_free", "hwbrj_ipc_export", "hwbrj_ipc_open",
@@ -104,6 +104,10 @@ def load():
     L.hwbrj_bloom_build.argtypes = [C.c_void_p, C.c_uint64, argp, C.c_uint32, C.c_void_p]
     L.hwbrj_bloom_probe.restype = C.c_int64
     L.hwbrj_bloom_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, argp, C.c_uint32, C.c_void_p]
+    L.hwbrj_materialize_last.restype = C.c_int64
+    L.hwbrj_materialize_last.argtypes = [C.c_void_p, C.c_uint64]
+    L.hwbrj_materialize_last_device.restype = C.c_int64
+    L.hwbrj_materialize_last_device.argtypes = [C.c_void_p, C.c_uint64]
     L.hwbrj_fpr_count.restype = C.c_int64
     L.hwbrj_fpr_count.argtypes = [C.c_void_p, C.c_void_p, argp, C.c_uint32]
     L.hwbrj_radix_partition.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]

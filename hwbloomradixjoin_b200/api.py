@@ -225,6 +225,17 @@ def join_device(R: DeviceRelation, S: DeviceRelation, bloom: BloomFilterArgs | N
                       st.checksum_key, st.as_dict())
 
 
+def materialize_last(expected: int) -> np.ndarray:
+    """Output pairs {key = R.payload, payload = S.payload} of the most recent join (JOIN_RESULT_MATERIALIZE, :307-312)"""
+    out = np.empty(max(int(expected), 0), dtype=TUPLE)
+    n = N.load().hwbrj_materialize_last(out.ctypes.data_as(C.c_void_p), out.shape[0])
+    if n < 0:
+        raise RuntimeError("no join to materialise")
+    if n > out.shape[0]:
+        return materialize_last(n)
+    return out[:n]
+
+
 def fpr_count(R: DeviceRelation, S: DeviceRelation, bloom: BloomFilterArgs, seed: int) -> int:
     """test_bloom_fpr (unit_tests.c:191-241) on the device: filter built with `seed` from R, number of S keys passing"""
     bloom.check()

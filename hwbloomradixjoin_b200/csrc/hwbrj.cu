@@ -68,6 +68,8 @@ struct Control {
     JoinAccum acc;
     uint32_t item_counter;
     uint32_t pad[3];
+    unsigned long long pair_cursor;  // materialised output pairs
+    unsigned long long pad2;
 };
 
 struct Ctx {
@@ -83,6 +85,12 @@ struct Ctx {
     DevBuf cur1b, cur2b, tilesb;          // second set of scatter cursors: R partitioning may overlap the S probe
     cudaStream_t side_stream = nullptr;   // R partitioning runs here while K2 runs on the main stream
     cudaEvent_t ev_side[4];
+    // state of the most recent join's partitions (inputs of a materialising k_join pass)
+    const uint2* last_Rp = nullptr;
+    const uint2* last_Sp = nullptr;
+    uint32_t last_P = 0, last_bits = 0;
+    bool last_hash = false;
+    DevBuf pairs;
     bool hash_partition = true;           // BASIC k<=1: partition on the filter-slice index, build the filter in smem
     bool hash_partition_force = false;    // HWBRJ_HASH_PARTITION=2: also for small filters (tests)
     bool overlap_r_partition = false;     // measured: the scatter traffic evicts the probed filter range (C1: 11.1 vs 9.9 ms)
@@ -125,6 +133,8 @@ static void init_ctx() {
     CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     CK(cudaFuncSetAttribute(k_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
     CK(cudaFuncSetAttribute(k_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
+    CK(cudaFuncSetAttribute(k_join<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
+    CK(cudaFuncSetAttribute(k_join<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
     if (const char* s = getenv("HWBRJ_RADIX_BITS")) g.radix_bits_override = atoi(s);
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
@@ -478,6 +488,11 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
             Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
             &ctrl->item_counter, &ctrl->acc);
     launches++;
+    g.last_Rp = Rp;
+    g.last_Sp = Sp;
+    g.last_P = P;
+    g.last_bits = (uint32_t)bits;
+    g.last_hash = pf.hash;
     CK(cudaEventRecord(g.ev[6], g.stream));
     Control h;
     CK(cudaMemcpyAsync(&h, ctrl, sizeof(Control), cudaMemcpyDeviceToHost, g.stream));
@@ -838,6 +853,48 @@ int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_
     if (survivors_out && cnt) CK(cudaMemcpy(survivors_out, g.sc.p, cnt * 8, cudaMemcpyDeviceToHost));
     CK(cudaGetLastError());
     return (int64_t)cnt;
+}
+
+// Materialise the output of the most recent join: re-runs only the per-partition build+probe (K5) over the
+// partitions that join left in the workspace, writing one {R.payload, S.payload} tuple per match
+// (bucket_chaining_join under JOIN_RESULT_MATERIALIZE, :307-312). Returns the number of pairs (which may exceed
+// `capacity`: then only the first `capacity` slots were written and the caller retries with a larger buffer).
+static int64_t materialize_last(uint2* d_pairs, uint64_t capacity) {
+    if (!g.last_Rp || !g.last_Sp) return -1;
+    Control* ctrl = g.ctrl.as<Control>();
+    CK(cudaMemsetAsync(&ctrl->acc, 0, sizeof(JoinAccum), g.stream));
+    CK(cudaMemsetAsync(&ctrl->item_counter, 0, sizeof(uint32_t), g.stream));
+    CK(cudaMemsetAsync(&ctrl->pair_cursor, 0, sizeof(unsigned long long), g.stream));
+    const int smem = kTableCap * (8 + 4 + 2);
+    if (g.last_hash)
+        k_join<true, true><<<g.sms * g.occ_join, kJoinThreads, smem, g.stream>>>(
+            g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.last_P,
+            g.last_bits, &ctrl->item_counter, &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
+    else
+        k_join<false, true><<<g.sms * g.occ_join, kJoinThreads, smem, g.stream>>>(
+            g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.last_P,
+            g.last_bits, &ctrl->item_counter, &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, &ctrl->pair_cursor, 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    return (int64_t)cnt;
+}
+
+int64_t hwbrj_materialize_last(tuple_t* pairs_out, uint64_t capacity) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!pairs_out && capacity) return -1;
+    g.pairs.ensure(std::max<uint64_t>(capacity, 1) * 8);
+    int64_t n = materialize_last(g.pairs.as<uint2>(), capacity);
+    if (n > 0) CK(cudaMemcpy(pairs_out, g.pairs.p, std::min<uint64_t>((uint64_t)n, capacity) * 8, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int64_t hwbrj_materialize_last_device(void* d_pairs, uint64_t capacity) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    return materialize_last(reinterpret_cast<uint2*>(d_pairs), capacity);
 }
 
 // device analogue of the reference's FPR measurement (test_bloom_fpr, unit_tests.c:191-241): build a filter with the

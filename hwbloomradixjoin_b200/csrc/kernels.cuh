@@ -743,11 +743,17 @@ __global__ void __launch_bounds__(1024) k_worklist(const uint32_t* __restrict__ 
 // chain counts. R partitions larger than kTableCap are processed in rounds; S partitions larger than kSChunk are
 // split over several work items (each rebuilds the table) so that skewed S does not serialise on one SM.
 // HASHPART: partitions come from the hash (filter-slice) partitioning, so the table index is key & (N-1).
-template <bool HASHPART>
+// PAIRS: materialise the output like -DJOIN_RESULT_MATERIALIZE does (:307-312): one {R.payload, S.payload} tuple per
+// match, appended to pairs_out through a warp-aggregated atomic cursor; pairs beyond pair_capacity are dropped (the
+// count stays exact, the caller retries with a larger buffer).
+template <bool HASHPART, bool PAIRS = false>
 __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
                                                       const uint2* __restrict__ Sp, const uint32_t* __restrict__ s_off,
                                                       const uint32_t* __restrict__ work_off, uint32_t P, uint32_t bits,
-                                                      uint32_t* __restrict__ item_counter, JoinAccum* __restrict__ acc_out) {
+                                                      uint32_t* __restrict__ item_counter, JoinAccum* __restrict__ acc_out,
+                                                      uint2* __restrict__ pairs_out = nullptr,
+                                                      unsigned long long* __restrict__ pair_cursor = nullptr,
+                                                      unsigned long long pair_capacity = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* tab = reinterpret_cast<uint2*>(smem_raw);                  // kTableCap tuples
     uint32_t* head = reinterpret_cast<uint32_t*>(tab + kTableCap);    // kTableCap heads (index+1, 0 = empty)
@@ -821,6 +827,15 @@ __global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__
                         for (uint32_t hit = head[(HASHPART ? s.x : (s.x >> bits)) & nmask]; hit; hit = next[hit - 1u]) {
                             uint2 r = tab[hit - 1u];
                             if (r.x == s.x) {
+                                if (PAIRS) {
+                                    const uint32_t am = __activemask();
+                                    const uint32_t lane = threadIdx.x & 31u;
+                                    const int leader = __ffs(am) - 1;
+                                    unsigned long long pos = 0ull;
+                                    if ((int)lane == leader) pos = atomicAdd(pair_cursor, (unsigned long long)__popc(am));
+                                    pos = __shfl_sync(am, pos, leader) + __popc(am & ((1u << lane) - 1u));
+                                    if (pos < pair_capacity) pairs_out[pos] = make_uint2(r.y, s.y);
+                                }
                                 matches++;
                                 cpair += mix64(r.y, s.y);
                                 crpay += r.y;

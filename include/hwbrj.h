@@ -182,6 +182,11 @@ int hwbrj_bloom_build(const tuple_t * R, uint64_t nR, const bloom_filter_args_t 
  * (any order) and their number (bloom_filter.c:93-111,135-141) */
 int64_t hwbrj_bloom_probe(const unsigned char * bitmap, const tuple_t * S, uint64_t nS,
                           const bloom_filter_args_t * args, uint32_t seed, tuple_t * survivors_out);
+/* Result materialisation (the reference's -DJOIN_RESULT_MATERIALIZE, parallel_radix_join_bloom.c:307-312): writes the
+ * output of the most recent join of this process as tuples {key = R.payload, payload = S.payload}, in any order.
+ * Returns the number of output pairs; if it exceeds `capacity` only `capacity` pairs were written (retry larger). */
+int64_t hwbrj_materialize_last(tuple_t * pairs_out /* host */, uint64_t capacity);
+int64_t hwbrj_materialize_last_device(void * d_pairs /* device */, uint64_t capacity);
 /* device analogue of the reference's FPR measurement (test_bloom_fpr, unit_tests.c:191-241): build a filter with
  * `seed` from the device-resident R, probe the device-resident S, return the number of passing S keys */
 int64_t hwbrj_fpr_count(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args, uint32_t seed);

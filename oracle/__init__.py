@@ -72,6 +72,9 @@ def lib():
                                        C.c_uint64, C.c_uint32, C.c_void_p]
         L.orc_join.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64,
                                C.c_uint64, C.c_uint64, C.c_int, C.POINTER(OrcResult)]
+        L.orc_join_pairs.restype = C.c_int64
+        L.orc_join_pairs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64,
+                                     C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64]
         L.orc_gen_relation.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_double,
                                        C.c_uint64]
         L.orc_gen_zipf.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_uint]
@@ -142,6 +145,18 @@ def join(R: np.ndarray, S: np.ndarray, bloom: bool, variant: int = 0, m: int = 1
     if rc != 0:
         raise MemoryError("orc_join failed")
     return {f: getattr(res, f) for f, _ in OrcResult._fields_}
+
+
+def join_pairs(R: np.ndarray, S: np.ndarray, bloom: bool, variant: int = 0, m: int = 1 << 28, k: int = 8, B: int = 1024,
+               capacity: int = 1 << 22) -> np.ndarray:
+    """materialised output {key = R.payload, payload = S.payload} (:307-312)"""
+    pairs = np.empty(capacity, dtype=TUPLE)
+    n = lib().orc_join_pairs(_tp(R), R.shape[0], _tp(S), S.shape[0], int(bloom), variant, m, k, B, 10, _tp(pairs), capacity)
+    if n < 0:
+        raise MemoryError("orc_join_pairs failed")
+    if n > capacity:
+        return join_pairs(R, S, bloom, variant, m, k, B, n)
+    return pairs[:n]
 
 
 def gen_relation(n: int, nthreads: int, maxid: int, threshold: int, selectivity: float, shuffle_seed: int) -> np.ndarray:

@@ -328,6 +328,10 @@ mix64(uint32_t rpay, uint32_t spay)
 /** bucket_chaining_join (:260-329): N = next pow2 >= numR, MASK = (N-1) << radix_bits,
  *  next[i] = bucket[idx]; bucket[idx] = i+1; probe walks the chain and counts every equal key.
  *  The output pair is (R.payload, S.payload) (:307-312). */
+/* optional materialisation target of bucket_chaining_join (the JOIN_RESULT_MATERIALIZE branch, :307-312) */
+static orc_tuple_t * g_pairs     = NULL;
+static uint64_t      g_pairs_cap = 0, g_pairs_n = 0;
+
 static void
 bucket_chaining_join(const orc_tuple_t * R, uint32_t numR, const orc_tuple_t * S, uint32_t numS,
                      int radix_bits, orc_result_t * acc)
@@ -353,6 +357,13 @@ bucket_chaining_join(const orc_tuple_t * R, uint32_t numR, const orc_tuple_t * S
         uint32_t idx = HBM(S[i].key, MASK, radix_bits);
         for (int32_t hit = bucket[idx]; hit > 0; hit = next[hit - 1]) {
             if (S[i].key == R[hit - 1].key) {
+                if (g_pairs) { /* joinres->key = R-rid; joinres->payload = S-rid (:310-311) */
+                    if (g_pairs_n < g_pairs_cap) {
+                        g_pairs[g_pairs_n].key     = R[hit - 1].payload;
+                        g_pairs[g_pairs_n].payload = S[i].payload;
+                    }
+                    g_pairs_n++;
+                }
                 acc->matches++;
                 acc->checksum_pair += mix64((uint32_t) R[hit - 1].payload, (uint32_t) S[i].payload);
                 acc->checksum_rpay += (uint32_t) R[hit - 1].payload;
@@ -429,6 +440,20 @@ orc_join(const orc_tuple_t * R, uint64_t nR, const orc_tuple_t * S, uint64_t nS,
     free(bitmap);
     free(surv);
     return 0;
+}
+
+/** orc_join that also materialises the output pairs {R.payload, S.payload}; returns the number of pairs */
+int64_t
+orc_join_pairs(const orc_tuple_t * R, uint64_t nR, const orc_tuple_t * S, uint64_t nS, int bloom_enable, int variant,
+               uint64_t m, uint64_t k, uint64_t B, int radix_bits, orc_tuple_t * pairs, uint64_t cap)
+{
+    orc_result_t res;
+    g_pairs     = pairs;
+    g_pairs_cap = cap;
+    g_pairs_n   = 0;
+    int rc      = orc_join(R, nR, S, nS, bloom_enable, variant, m, k, B, radix_bits, &res);
+    g_pairs     = NULL;
+    return rc ? -1 : (int64_t) g_pairs_n;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -272,6 +272,32 @@ def test_empty_and_ragged_inputs(Hgpu, oracle_mod, nr, ns):
     assert res.totalresults == oracle_mod.join(R, S, False)["matches"]
 
 
+def test_result_materialisation(Hgpu, oracle_mod):
+    """the output pairs {R.payload, S.payload} (JOIN_RESULT_MATERIALIZE, :307-312) as a multiset"""
+    rng = np.random.default_rng(9)
+    R = np.zeros(150_000, dtype=Hgpu.TUPLE)
+    R["key"] = rng.integers(1, 60_000, R.shape[0]).astype(np.int32)  # duplicate build keys: several pairs per S tuple
+    R["payload"] = np.arange(R.shape[0])
+    S = np.zeros(400_000, dtype=Hgpu.TUPLE)
+    S["key"] = rng.integers(1, 120_000, S.shape[0]).astype(np.int32)
+    S["payload"] = np.arange(S.shape[0]) + 7_000_000
+    for args, oargs in [(None, (False,)), (Hgpu.BloomFilterArgs(0, 1 << 20, 1, 512), (True, 0, 1 << 20, 1, 512)),
+                        (Hgpu.BloomFilterArgs(1, 1 << 20, 3, 256), (True, 1, 1 << 20, 3, 256))]:
+        res = Hgpu.run("PRO", R, S, 1, args)
+        exp = oracle_mod.join_pairs(R, S, *oargs)
+        assert res.totalresults == exp.shape[0]
+        got = Hgpu.materialize_last(16)  # too small on purpose: the count comes back and the call retries
+        assert got.shape[0] == exp.shape[0]
+        assert (sort_tuples(got) == sort_tuples(exp)).all()
+    Hgpu.set_hash_partition(2)
+    try:
+        res = Hgpu.run("PRO", R, S, 1, Hgpu.BloomFilterArgs(0, 1 << 20, 1, 512))
+        got = Hgpu.materialize_last(res.totalresults)
+        assert (sort_tuples(got) == sort_tuples(oracle_mod.join_pairs(R, S, True, 0, 1 << 20, 1, 512))).all()
+    finally:
+        Hgpu.set_hash_partition(1)
+
+
 def test_device_resident_join_matches_host_buffer_join(Hgpu, oracle_mod):
     R, S = inputs(oracle_mod, 250_000, 2_000_000, 0.01)
     dR, dS = Hgpu.DeviceRelation.upload(R), Hgpu.DeviceRelation.upload(S)
