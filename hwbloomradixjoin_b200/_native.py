@@ -46,7 +46,7 @@ class StatsT(C.Structure):  # hwbrj_stats_t
 
 # every symbol include/hwbrj.h declares (tests check that the library exports all of them)
 EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_last_stats", "hwbrj_last_filtered",
-           "hwbrj_last_checksum", "hwbrj_last_filter", "hwbrj_set_quiet", "hwbrj_set_radix_bits", "hwbrj_set_range_passes", "hwbrj_set_hash_partition", "hwbrj_version",
+           "hwbrj_last_checksum", "hwbrj_last_filter", "hwbrj_set_quiet", "hwbrj_set_radix_bits", "hwbrj_set_range_passes", "hwbrj_set_overlap_h2d", "hwbrj_set_hash_partition", "hwbrj_version",
            "hwbrj_device_count", "hwbrj_check_args", "hwbrj_rel_upload", "hwbrj_rel_generate", "hwbrj_rel_download",
            "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_host_alloc", "hwbrj_host_free",
            "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_fpr_count", "hwbrj_materialize_last", "hwbrj_materialize_last_device", "hwbrj_radix_partition",
@@ -86,6 +86,7 @@ def load():
     L.hwbrj_set_radix_bits.argtypes = [C.c_int]
     L.hwbrj_set_range_passes.argtypes = [C.c_int]
     L.hwbrj_set_hash_partition.argtypes = [C.c_int]
+    L.hwbrj_set_overlap_h2d.argtypes = [C.c_int]
     L.hwbrj_version.restype = C.c_char_p
     L.hwbrj_check_args.argtypes = [argp]
     L.hwbrj_rel_upload.restype = C.c_void_p

@@ -91,6 +91,10 @@ struct Ctx {
     uint32_t last_P = 0, last_bits = 0;
     bool last_hash = false;
     DevBuf pairs;
+    // host-buffer calls: upload S in chunks on a copy stream and probe each chunk as soon as it has landed
+    bool overlap_h2d = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[66];
     bool hash_partition = true;           // BASIC k<=1: partition on the filter-slice index, build the filter in smem
     bool hash_partition_force = false;    // HWBRJ_HASH_PARTITION=2: also for small filters (tests)
     bool overlap_r_partition = false;     // measured: the scatter traffic evicts the probed filter range (C1: 11.1 vs 9.9 ms)
@@ -122,6 +126,9 @@ static void init_ctx() {
     g.stream = g.own_stream;
     for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
     CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : g.ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char* s = getenv("HWBRJ_OVERLAP_H2D")) g.overlap_h2d = atoi(s) != 0;
     for (auto& ev : g.ev_side) CK(cudaEventCreate(&ev));
     if (const char* s = getenv("HWBRJ_OVERLAP")) g.overlap_r_partition = atoi(s) != 0;
     CrcTables T;
@@ -371,9 +378,16 @@ static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t
 }
 
 // The join on device-resident relations. args == nullptr: plain radix join.
+// S arriving from the host in chunks: chunk c (chunk_tuples tuples, the last one shorter) is complete when ev[c] fires
+struct SFeed {
+    uint64_t chunk_tuples;
+    int nchunks;
+    cudaEvent_t* ev;
+};
+
 static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS, const bloom_filter_args_t* args,
                      hwbrj_stats_t& st, const unsigned long long* nR_dev = nullptr, uint64_t nR_expect = 0,
-                     const unsigned long long* nS_dev = nullptr) {
+                     const unsigned long long* nS_dev = nullptr, const SFeed* feed = nullptr) {
     // nR/nS are exact counts, or capacities when the real counts live on the device (nR_dev/nS_dev)
     if (nR >= (1ull << 32) || nS >= (1ull << 32)) die("relations of 2^32 or more tuples are not supported");
     if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
@@ -459,8 +473,18 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     const unsigned long long* n_dev = nS_dev;
     if (args) {
         if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(nS, 1) * 8);
-        launches += run_probe(dS, nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
-                              nranges > 2 ? g.d1.as<uint2>() : nullptr);
+        if (feed) {  // probe every chunk as soon as its host->device copy has completed
+            for (int c = 0; c < feed->nchunks; c++) {
+                const uint64_t off = (uint64_t)c * feed->chunk_tuples;
+                const uint64_t cnt = std::min<uint64_t>(feed->chunk_tuples, nS - off);
+                CK(cudaStreamWaitEvent(g.stream, feed->ev[c], 0));
+                launches += run_probe(dS + off, cnt, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
+                                      nranges > 2 ? g.d1.as<uint2>() : nullptr);
+            }
+        } else {
+            launches += run_probe(dS, nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
+                                  nranges > 2 ? g.d1.as<uint2>() : nullptr);
+        }
         Sin = g.sc.as<uint2>();
         n_dev = &ctrl->survivors;
     }
@@ -572,14 +596,36 @@ static result_t* host_join(relation_t* relR, relation_t* relS, int nthreads, blo
     const uint64_t nR = relR->num_tuples, nS = relS->num_tuples;
     g.inR.ensure(std::max<uint64_t>(nR, 2) * 8);
     g.inS.ensure(std::max<uint64_t>(nS, 2) * 8);
-    CK(cudaEventRecord(g.ev[7], g.stream));
-    h2d(g.inR.p, relR->tuples, nR * 8);
-    h2d(g.inS.p, relS->tuples, nS * 8);
-    CK(cudaEventRecord(g.ev[0], g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[7], g.ev[0]));
     st.h2d_bytes = (nR + nS) * 8;
-    run_join(g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, st);
+    if (g.overlap_h2d && args && nS >= (1u << 22)) {
+        // copies on their own stream; R first, then S in <= 64 chunks, each followed by an event the probe waits on
+        SFeed feed;
+        feed.nchunks = (int)std::min<uint64_t>(64, (nS + (1u << 22) - 1) >> 22);
+        feed.chunk_tuples = (((nS + feed.nchunks - 1) / feed.nchunks) + 1) & ~1ull;  // even: chunks stay 16-byte aligned
+        feed.nchunks = (int)((nS + feed.chunk_tuples - 1) / feed.chunk_tuples);
+        feed.ev = g.ev_chunk + 1;
+        CK(cudaEventRecord(g.ev[7], g.copy_stream));
+        if (nR) CK(cudaMemcpyAsync(g.inR.p, relR->tuples, nR * 8, cudaMemcpyHostToDevice, g.copy_stream));
+        CK(cudaEventRecord(g.ev_chunk[0], g.copy_stream));
+        for (int c = 0; c < feed.nchunks; c++) {
+            const uint64_t off = (uint64_t)c * feed.chunk_tuples;
+            const uint64_t cnt = std::min<uint64_t>(feed.chunk_tuples, nS - off);
+            CK(cudaMemcpyAsync(g.inS.as<uint2>() + off, relS->tuples + off, cnt * 8, cudaMemcpyHostToDevice, g.copy_stream));
+            CK(cudaEventRecord(feed.ev[c], g.copy_stream));
+        }
+        CK(cudaEventRecord(g.ev_side[3], g.copy_stream));
+        CK(cudaStreamWaitEvent(g.stream, g.ev_chunk[0], 0));  // the R phase needs all of R
+        run_join(g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, st, nullptr, 0, nullptr, &feed);
+        CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[7], g.ev_side[3]));
+    } else {
+        CK(cudaEventRecord(g.ev[7], g.stream));
+        h2d(g.inR.p, relR->tuples, nR * 8);
+        h2d(g.inS.p, relS->tuples, nS * 8);
+        CK(cudaEventRecord(g.ev[0], g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[7], g.ev[0]));
+        run_join(g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, st);
+    }
     st.ms_e2e = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     g.last = st;
     print_reference_lines(st, nS, args != nullptr && print_filtered);
@@ -641,6 +687,7 @@ uint64_t hwbrj_last_checksum(void) { return g.last.checksum_pair; }
 void hwbrj_set_quiet(int quiet) { g.quiet = quiet != 0; }
 void hwbrj_set_radix_bits(int bits) { g.radix_bits_override = bits; }
 void hwbrj_set_range_passes(int passes) { g.range_passes_override = passes; }
+void hwbrj_set_overlap_h2d(int on) { g.overlap_h2d = on != 0; }
 void hwbrj_set_hash_partition(int mode) {
     g.hash_partition = mode != 0;
     g.hash_partition_force = mode == 2;

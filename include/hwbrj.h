@@ -142,6 +142,9 @@ void hwbrj_set_quiet(int quiet);    /* 1: suppress the reference-style stdout li
 /* tuning knobs (also read from env HWBRJ_RADIX_BITS / HWBRJ_RANGE_PASSES); 0 = automatic */
 void hwbrj_set_radix_bits(int bits);
 void hwbrj_set_range_passes(int passes);
+/* host-buffer Bloom joins: upload S in chunks on a copy stream and probe each chunk as it lands (hides the join
+ * under the PCIe copy; TOTAL-TIME-USECS then includes waiting for the copies). Off by default. */
+void hwbrj_set_overlap_h2d(int on);
 /* partition the join on the filter-slice index and build the filter in shared memory (BASIC k<=1):
  * 0 never, 1 when the filter exceeds 32 MiB (default), 2 whenever the slices fit */
 void hwbrj_set_hash_partition(int mode);

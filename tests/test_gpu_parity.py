@@ -298,6 +298,21 @@ def test_result_materialisation(Hgpu, oracle_mod):
         Hgpu.set_hash_partition(1)
 
 
+def test_chunked_upload_overlapped_with_probe(Hgpu, oracle_mod):
+    """host-buffer call with the S upload split into chunks that are probed as they land"""
+    from hwbloomradixjoin_b200 import _native as N
+    R = oracle_mod.gen_R(600_000, nthreads=4)
+    S = oracle_mod.gen_S(9_000_001, 600_000, 0.02, nthreads=4)
+    for variant, m, k, B in [(0, 1 << 23, 1, 512), (1, 1 << 23, 3, 256), (0, 1 << 23, 2, 512)]:
+        exp = oscalars(oracle_mod.join(R, S, True, variant, m, k, B))
+        N.load().hwbrj_set_overlap_h2d(1)
+        try:
+            got = Hgpu.BPRO(R, S, 1, Hgpu.BloomFilterArgs(variant, m, k, B))
+        finally:
+            N.load().hwbrj_set_overlap_h2d(0)
+        assert scalars(got) == exp
+
+
 def test_device_resident_join_matches_host_buffer_join(Hgpu, oracle_mod):
     R, S = inputs(oracle_mod, 250_000, 2_000_000, 0.01)
     dR, dS = Hgpu.DeviceRelation.upload(R), Hgpu.DeviceRelation.upload(S)
