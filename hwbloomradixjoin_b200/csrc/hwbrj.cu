@@ -152,7 +152,7 @@ static void init_ctx() {
     CK(cudaFuncSetAttribute(k_scatter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-    CK(cudaFuncSetAttribute(k_filter_from_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_filter_from_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
     CK(cudaFuncSetAttribute(k_build_hist<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     if (const char* s = getenv("HWBRJ_HASH_PARTITION")) {
         g.hash_partition = atoi(s) != 0;
@@ -464,7 +464,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     CK(cudaEventRecord(g.ev_side[2], g.stream));
     if (pf.hash && args->k >= 1) {  // K1': the filter, slice by slice, from the partitioned R (k = 0 sets no bit)
         const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
-        k_filter_from_parts<<<g.sms * 4, 256, slice_words * 4, g.stream>>>(Rp, g.offR.as<uint32_t>(), P, g.filter.as<uint32_t>(),
+        k_filter_from_parts<<<g.sms * 4, 512, 2 * slice_words * 4, g.stream>>>(Rp, g.offR.as<uint32_t>(), P, g.filter.as<uint32_t>(),
                                                                           slice_words, 42u, pf.size_mask);
         launches++;
     }

@@ -671,23 +671,40 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
 // filter, S = m / 2^bits), every partition owns one contiguous slice: a CTA zeroes the slice in shared memory, ORs in
 // the bits of its partition's keys with shared-memory atomics and writes the slice out with coalesced stores. This
 // replaces add_generic's atomic OR per key (bloom_filter.c:74-89) for BASIC k = 1; the bitmap is byte-identical.
-__global__ void __launch_bounds__(256) k_filter_from_parts(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
+__global__ void __launch_bounds__(512) k_filter_from_parts(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
                                                           uint32_t P, uint32_t* __restrict__ filter, uint32_t slice_words,
                                                           uint32_t seed, uint32_t size_mask) {
-    extern __shared__ uint32_t s_slice[];
+    extern __shared__ uint32_t s_slice[];  // two slices: a CTA alternates so that only one barrier separates partitions
     const uint32_t slice_mask = slice_words * 32u - 1u;
-    for (uint32_t p = blockIdx.x; p < P; p += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) s_slice[i] = 0u;
-        __syncthreads();
+    const uint64_t pol = policy_evict_first();
+    constexpr int U = 4;  // independent loads in flight per thread
+    for (uint32_t i = threadIdx.x; i < 2 * slice_words; i += blockDim.x) s_slice[i] = 0u;
+    __syncthreads();
+    uint32_t par = 0;
+    for (uint32_t p = blockIdx.x; p < P; p += gridDim.x, par ^= 1u) {
+        uint32_t* sl = s_slice + par * slice_words;
         const uint32_t lo = r_off[p], hi = r_off[p + 1];
-        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const uint32_t h = hash_crapwow(seed, Rp[i].x) & size_mask & slice_mask;
-            atomicOr(&s_slice[h >> 5], 1u << (h & 31u));
+        for (uint32_t i0 = lo + threadIdx.x; i0 < hi; i0 += U * blockDim.x) {
+            uint32_t key[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+                key[u] = i < hi ? ld_stream_v2(Rp + i, pol).x : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (i0 + u * blockDim.x < hi) {
+                    const uint32_t h = hash_crapwow(seed, key[u]) & size_mask & slice_mask;
+                    atomicOr(&sl[h >> 5], 1u << (h & 31u));
+                }
+            }
         }
-        __syncthreads();
+        __syncthreads();  // slice complete
         uint32_t* dst = filter + (uint64_t)p * slice_words;
-        for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) dst[i] = s_slice[i];
-        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) {
+            dst[i] = sl[i];
+            sl[i] = 0u;  // ready for the partition after next; the next partition uses the other buffer meanwhile
+        }
     }
 }
 
