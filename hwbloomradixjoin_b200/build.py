@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libhwbrj_cuda.so")
-SRC = [os.path.join(HERE, "csrc", f) for f in ("hwbrj.cu", "kernels.cuh", "hash.cuh", "dist.cuh")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("hwbrj.cu", "kernels.cuh", "hash.cuh")]
 HDR = os.path.join(ROOT, "include", "hwbrj.h")
 DRIVER_SRC = os.path.join(ROOT, "host", "mchashjoins_gpu.c")
 DRIVER = os.path.join(ROOT, "build", "mchashjoins_gpu")

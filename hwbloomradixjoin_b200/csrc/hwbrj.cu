@@ -14,7 +14,6 @@
 
 #include "../../include/hwbrj.h"
 #include "kernels.cuh"
-#include "dist.cuh"
 
 namespace hwbrj {
 
@@ -105,7 +104,7 @@ struct Ctx {
     int probe_ctas_per_sm = 0;  // 0 = occupancy API
     bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
     DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
-    int occ_probe = 1, occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
+    int occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
     std::mutex mu;
 };
 
@@ -299,10 +298,6 @@ static int run_probe(const uint2* dS, uint64_t nS, BloomParams bp, int nranges, 
     return nranges;
 }
 
-struct Partitioned {
-    const uint2* data;
-    const uint32_t* off;
-};
 
 // histogram already in `hist`; runs scan + 1 or 2 scatter passes. n_dev (optional) = device-side tuple count.
 // Partition function of the join: key & (2^bits-1) (the reference's radix clustering), or -- for a BASIC k<=1 filter

@@ -99,6 +99,17 @@ def test_bitmap_kat_from_reference(Hgpu):
         assert Hgpu.bloom_probe(bm, S, args) == row["pass"]
 
 
+@pytest.mark.parametrize("variant,lgm,k,B", [(0, 31, 1, 512), (0, 32, 1, 512), (0, 32, 2, 512), (1, 32, 3, 512)])
+def test_largest_filters(Hgpu, oracle_mod, variant, lgm, k, B):
+    """A.5: the reference's uint32 size arithmetic allows m up to 2^32 (512 MiB, 8 filter range passes here)"""
+    R, S = inputs(oracle_mod, 250_000, 2_000_000, 0.01)
+    m = 1 << lgm
+    res = Hgpu.BPRO(R, S, 1, Hgpu.BloomFilterArgs(variant, m, k, B))
+    assert scalars(res) == oscalars(oracle_mod.join(R, S, True, variant, m, k, B))
+    if k == 1 and variant == 0:
+        assert res.stats["range_passes"] == (m // 8) // (64 << 20)
+
+
 def test_filter_full_range_keys(Hgpu, oracle_mod):
     rng = np.random.default_rng(11)
     R = np.zeros(100_001, dtype=Hgpu.TUPLE)

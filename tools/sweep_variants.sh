@@ -1,7 +1,6 @@
 #!/bin/bash
-# times every tuning variant in build/variants on C1 (development helper)
+# development helper: time every tuning variant (build/variants/lib_*.so, compiled with -DHWBRJ_* overrides) on a workload
+w=${1:-c1}
 for lib in build/variants/lib_*.so; do
-  for c in 2 3 4 6; do
-  echo "$(basename $lib) ctas=$c: $(HWBRJ_PROBE_CTAS=$c HWBRJ_LIB=$PWD/$lib python tools/prof_c1.py c1 3 | tail -1 | sed 's/matches=[0-9]* filtered=-\?[0-9]* //')"
-  done
+  echo "$(basename $lib): $(HWBRJ_LIB=$PWD/$lib python tools/prof_c1.py $w 3 | tail -1 | sed 's/matches=[0-9]* filtered=-\?[0-9]* //')"
 done
