@@ -5,6 +5,8 @@ from __future__ import annotations
 
 import json
 import os
+import sys
+import threading
 import statistics
 import time
 
@@ -20,6 +22,9 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
         if rank == 0:
             print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with one rank per GPU"}))
         return 1
+    watchdog = threading.Timer(float(os.environ.get("HWBRJ_BENCH_WATCHDOG_S", "420")), lambda: os._exit(3))
+    watchdog.daemon = True  # never let a stuck rank hold the box
+    watchdog.start()
     # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything else goes to stderr
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -27,7 +32,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
     from . import BloomFilterArgs
-    from .dist import CudaOps, PeerFabric, dist_join, dist_join_peer
+    from .dist import CudaOps, PeerFabric, PeerJoinGraph, dist_join, dist_join_peer
     ops = CudaOps(device)
     r, s, q, variant, m, k, B, desc = wl
     bloom = BloomFilterArgs(variant, m, k, B) if variant is not None else None
@@ -54,8 +59,26 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
         out["path"] = "nccl-all-to-all"
         return out
 
+    # device-resident leg: the whole collective join replayed as one CUDA graph (kernels + NVLink stores + NCCL)
+    graph = None
+    if fabric is not None and os.environ.get("HWBRJ_DIST_GRAPH", "1") == "1":
+        try:
+            graph = PeerJoinGraph(ops, fabric, Rsh, Ssh, bloom, r, s)
+            if graph.replay() is None:
+                graph = None
+        except Exception as exc:  # capture not possible here: run the eager pipeline
+            print(f"[bench] CUDA graph capture unavailable ({exc}); using the eager pipeline", flush=True)
+            graph = None
+
+    def resident_step():
+        if graph is not None:
+            out = graph.replay()
+            if out is not None:
+                return out
+        return step(Rsh, Ssh)
+
     for _ in range(max(args.warmup, 3)):
-        res = step(Rsh, Ssh)
+        res = resident_step()
     sampler = ClockSampler(local)
     dist.barrier()
     torch.cuda.synchronize()
@@ -65,7 +88,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        res = step(Rsh, Ssh)
+        res = resident_step()
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -130,10 +153,12 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
                 "e2e": {"value": (r + s) / e2e_t.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (r + s),
                         "d2h_bytes_per_step": 8 * 16 * world, "ms_per_step": e2e_t.item() * 1e3, "steps": e2e_steps,
                         "api": "hwbloomradixjoin_b200.dist.dist_join on pinned host shards"},
-                "gpu_launches": int(args.steps * world * (phased["local"]["kernel_launches"] + 8)), "clocks": clocks}
+                "gpu_launches": int(args.steps * world * (phased["local"]["kernel_launches"] + 8)), "clocks": clocks,
+                "cuda_graph": graph is not None}
         os.write(saved_stdout, (json.dumps(line) + "\n").encode())
-    if fabric is not None:
-        fabric.close()
-    dist.barrier()
-    dist.destroy_process_group()
-    return 0
+    # No collective teardown: every rank has passed the last all-reduce, rank 0 has printed its line. Tearing down the
+    # captured graph, the IPC mappings and the NCCL communicator in lock step gains nothing here and a rank that
+    # waits for a peer which is already gone would hang the launcher, so the processes simply exit.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)

@@ -373,6 +373,18 @@ static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t
 }
 
 // The join on device-resident relations. args == nullptr: plain radix join.
+// copies the result words of a join out of the control block (async / graph-captured joins)
+__global__ void k_export_results(const Control* c, unsigned long long* out) {
+    if (threadIdx.x == 0) {
+        out[0] = c->acc.matches;
+        out[1] = c->acc.cpair;
+        out[2] = c->acc.crpay;
+        out[3] = c->acc.cspay;
+        out[4] = c->acc.ckey;
+        out[5] = c->survivors;
+    }
+}
+
 // S arriving from the host in chunks: chunk c (chunk_tuples tuples, the last one shorter) is complete when ev[c] fires
 struct SFeed {
     uint64_t chunk_tuples;
@@ -382,7 +394,14 @@ struct SFeed {
 
 static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS, const bloom_filter_args_t* args,
                      hwbrj_stats_t& st, const unsigned long long* nR_dev = nullptr, uint64_t nR_expect = 0,
-                     const unsigned long long* nS_dev = nullptr, const SFeed* feed = nullptr) {
+                     const unsigned long long* nS_dev = nullptr, const SFeed* feed = nullptr,
+                     unsigned long long* d_async_out = nullptr) {
+    // d_async_out != nullptr: enqueue only (no events, no host synchronisation -- capturable in a CUDA graph); the six
+    // result words {matches, cpair, crpay, cspay, ckey, survivors} are left in d_async_out (device)
+    const bool async_mode = d_async_out != nullptr;
+    auto rec = [&](cudaEvent_t e, cudaStream_t s) {
+        if (!async_mode) CK(cudaEventRecord(e, s));
+    };
     // nR/nS are exact counts, or capacities when the real counts live on the device (nR_dev/nS_dev)
     if (nR >= (1ull << 32) || nS >= (1ull << 32)) die("relations of 2^32 or more tuples are not supported");
     if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
@@ -396,14 +415,14 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     Control* ctrl = g.ctrl.as<Control>();
 
     // ---- untimed set-up (the reference allocates and zeroes its filter before the timed region, :1583) ----
-    CK(cudaEventRecord(g.ev[0], g.stream));
+    rec(g.ev[0], g.stream);
     if (args) CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
     CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
     CK(cudaMemsetAsync(g.histS.p, 0, P * 4, g.stream));
     CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
 
     // ---- timed region ----------------------------------------------------------------------------------------
-    CK(cudaEventRecord(g.ev[1], g.stream));
+    rec(g.ev[1], g.stream);
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
     int nranges = 1;
@@ -442,28 +461,28 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
         launches++;
     }
-    CK(cudaEventRecord(g.ev[2], g.stream));
+    rec(g.ev[2], g.stream);
     // R partitioning (HBM-bound) runs on a side stream underneath the S probe (L1TEX/issue-bound) when a filter is used
     const bool overlap = g.overlap_r_partition && args != nullptr;
     const uint2* Rp;
     if (overlap) {
         CK(cudaStreamWaitEvent(g.side_stream, g.ev[2], 0));
-        CK(cudaEventRecord(g.ev_side[0], g.side_stream));
+        rec(g.ev_side[0], g.side_stream);
         Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(), g.rt1.as<uint2>(),
                            g.rp.as<uint2>(), launches, g.side_stream, true);
-        CK(cudaEventRecord(g.ev_side[1], g.side_stream));
+        rec(g.ev_side[1], g.side_stream);
     } else {
         Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(), g.rt1.as<uint2>(),
                            g.rp.as<uint2>(), launches, nullptr, false, pf);
     }
-    CK(cudaEventRecord(g.ev_side[2], g.stream));
+    rec(g.ev_side[2], g.stream);
     if (pf.hash && args->k >= 1) {  // K1': the filter, slice by slice, from the partitioned R (k = 0 sets no bit)
         const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
         k_filter_from_parts<<<g.sms * 4, 512, 2 * slice_words * 4, g.stream>>>(Rp, g.offR.as<uint32_t>(), P, g.filter.as<uint32_t>(),
                                                                           slice_words, 42u, pf.size_mask);
         launches++;
     }
-    CK(cudaEventRecord(g.ev[3], g.stream));
+    rec(g.ev[3], g.stream);
     const uint2* Sin = dS;
     const unsigned long long* n_dev = nS_dev;
     if (args) {
@@ -490,11 +509,11 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     else
         k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
     launches++;
-    CK(cudaEventRecord(g.ev[4], g.stream));
+    rec(g.ev[4], g.stream);
     // with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc
     const uint2* Sp = run_partition(Sin, nS, n_dev, bits, b2, g.histS.as<uint32_t>(), g.offS.as<uint32_t>(),
                                     g.st1.as<uint2>(), g.sc.as<uint2>(), launches, nullptr, false, pf);
-    CK(cudaEventRecord(g.ev[5], g.stream));
+    rec(g.ev[5], g.stream);
     if (overlap) CK(cudaStreamWaitEvent(g.stream, g.ev_side[1], 0));
     k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>());
     launches++;
@@ -512,7 +531,14 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     g.last_P = P;
     g.last_bits = (uint32_t)bits;
     g.last_hash = pf.hash;
-    CK(cudaEventRecord(g.ev[6], g.stream));
+    rec(g.ev[6], g.stream);
+    if (async_mode) {
+        k_export_results<<<1, 32, 0, g.stream>>>(ctrl, d_async_out);
+        st.kernel_launches = launches + 1;
+        st.radix_bits = bits;
+        st.range_passes = nranges;
+        return;
+    }
     Control h;
     CK(cudaMemcpyAsync(&h, ctrl, sizeof(Control), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -812,6 +838,17 @@ int hwbrj_join_device(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_fi
     g.last = st;
     if (out) *out = st;
     return 0;
+}
+
+int hwbrj_join_device_async(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out6) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!R || !S || !d_out6) return -1;
+    hwbrj_stats_t st;
+    memset(&st, 0, sizeof(st));
+    run_join(R->d, R->n, S->d, S->n, args, st, R->n_dev, R->n_expect, S->n_dev, nullptr,
+             reinterpret_cast<unsigned long long*>(d_out6));
+    return st.kernel_launches;
 }
 
 void* hwbrj_host_alloc(uint64_t bytes) {

@@ -415,3 +415,96 @@ def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Ssh
         torch.cuda.synchronize()
         out["phases_ms"] = tm.phases_ms()
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The same pipeline as ONE CUDA graph: kernels, NVLink peer stores, barriers, filter all-gather and the final
+# all-reduce are captured once and replayed per join, so there is no launch gap between the ~20 short kernels.
+# ----------------------------------------------------------------------------------------------------------------
+def _peer_pipeline_async(ops: "CudaOps", fabric: PeerFabric, Rshard, Sshard, bloom, r_total, s_total, keep):
+    """dist_join_peer without any host synchronisation: returns the all-reduced int64 vector (device)
+    [matches, filtered, cpair, crpay, cspay, ckey, overflow, r_owned, s_owned]. `keep` collects the tensors that
+    must stay alive as long as the captured graph."""
+    group, world = fabric.group, fabric.world
+    L = ops.L
+    L.hwbrj_set_stream(torch.cuda.current_stream(ops.device).cuda_stream)
+    is_sliced = sliceable(bloom, world)
+    slice_args = bloom if is_sliced else None
+    cargs = slice_args.to_c() if slice_args is not None else None
+    cref = C.byref(cargs) if cargs is not None else None
+    ctrl = fabric.local[2]  # set 0 only: the graph starts with an explicit reset + barrier
+    fabric.ctrl_view[0:4].zero_()
+    fabric.barrier()
+    h = ops._wrap(Rshard)
+    if L.hwbrj_route_peer(h, world, cref, fabric.ptr_array(0), fabric.ptr_array(2, 0), fabric.cap_r, ctrl + 16) != 0:
+        raise RuntimeError("hwbrj_route_peer(R) failed")
+    L.hwbrj_rel_free(h)
+    fabric.barrier()
+    Rown = L.hwbrj_rel_wrap_counted(fabric.local[0], fabric.cap_r, ctrl, max(r_total // world, 1))
+    cnt = torch.zeros(1, dtype=torch.int64, device=ops.device)
+    keep.append(cnt)
+    if bloom is not None:
+        filt = torch.empty(max(bloom.m // 8, 16), dtype=torch.uint8, device=ops.device)
+        bc = bloom.to_c()
+        if L.hwbrj_filter_build(Rown, C.byref(bc), filt.data_ptr(), 1) != 0:
+            raise RuntimeError("hwbrj_filter_build failed")
+        filt = combine_filter(ops, filt, bloom, is_sliced, group)
+        surv = ops.empty_tuples(Sshard.numel())
+        keep += [filt, surv]
+        hs = ops._wrap(Sshard)
+        if L.hwbrj_filter_probe_async(filt.data_ptr(), hs, C.byref(bc), surv.data_ptr(), cnt.data_ptr()) != 0:
+            raise RuntimeError("hwbrj_filter_probe_async failed")
+        L.hwbrj_rel_free(hs)
+        hsurv = L.hwbrj_rel_wrap_counted(surv.data_ptr(), surv.numel(), cnt.data_ptr(), surv.numel())
+    else:
+        hsurv = ops._wrap(Sshard)
+    if L.hwbrj_route_peer(hsurv, world, cref, fabric.ptr_array(1), fabric.ptr_array(2, 8), fabric.cap_s, ctrl + 16) != 0:
+        raise RuntimeError("hwbrj_route_peer(S) failed")
+    L.hwbrj_rel_free(hsurv)
+    fabric.barrier()
+    Sown = L.hwbrj_rel_wrap_counted(fabric.local[1], fabric.cap_s, ctrl + 8, max(s_total // world, 1))
+    out6 = torch.zeros(8, dtype=torch.int64, device=ops.device)
+    keep.append(out6)
+    launches = L.hwbrj_join_device_async(Rown, Sown, None, out6.data_ptr())
+    L.hwbrj_rel_free(Rown)
+    L.hwbrj_rel_free(Sown)
+    if launches < 0:
+        raise RuntimeError("hwbrj_join_device_async failed")
+    cv = fabric.ctrl_view
+    vec = torch.stack([out6[0], cnt[0], out6[1], out6[2], out6[3], out6[4], cv[2] & 0xFFFFFFFF, cv[0], cv[1]])
+    dist.all_reduce(vec, group=group)  # int64 lanes wrap modulo 2^64 exactly like the uint64 sums they carry
+    keep.append(vec)
+    return vec, is_sliced, launches
+
+
+class PeerJoinGraph:
+    """dist_join_peer captured as a CUDA graph for fixed shard tensors; replay() runs one join and returns the global
+    scalars (or None on receive-buffer overflow)."""
+
+    def __init__(self, ops: "CudaOps", fabric: PeerFabric, Rshard, Sshard, bloom, r_total, s_total):
+        if bloom is not None:
+            bloom.check()
+        self.ops, self.bloom, self.keep = ops, bloom, [Rshard, Sshard]
+        side = torch.cuda.Stream(device=ops.device)
+        side.wait_stream(torch.cuda.current_stream(ops.device))
+        with torch.cuda.stream(side):  # warm-up on a side stream: allocations, attributes, NCCL connections
+            for _ in range(2):
+                _peer_pipeline_async(ops, fabric, Rshard, Sshard, bloom, r_total, s_total, [])
+        torch.cuda.current_stream(ops.device).wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.vec, self.is_sliced, self.launches = _peer_pipeline_async(ops, fabric, Rshard, Sshard, bloom, r_total,
+                                                                           s_total, self.keep)
+        ops.L.hwbrj_set_stream(torch.cuda.current_stream(ops.device).cuda_stream)
+        self.world = fabric.world
+
+    def replay(self) -> Optional[dict]:
+        self.graph.replay()
+        v = [x & MASK64 for x in self.vec.tolist()]  # the only host synchronisation of the join
+        if v[6]:
+            return None
+        return {"matches": v[0], "filtered": v[1] if self.bloom is not None else -1, "checksum_pair": v[2],
+                "checksum_rpay": v[3], "checksum_spay": v[4], "checksum_key": v[5], "sliced_filter": self.is_sliced,
+                "world": self.world, "r_owned_total": v[7], "s_owned_total": v[8], "path": "nvlink-peer-stores+cuda-graph",
+                "local": {"kernel_launches": self.launches}}

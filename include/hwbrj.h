@@ -171,6 +171,11 @@ void     hwbrj_rel_free(hwbrj_rel_t * rel);
 int hwbrj_join_device(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
                       hwbrj_stats_t * out);
 
+/* enqueue-only variant (no events, no host synchronisation: can be captured in a CUDA graph together with the
+ * collectives around it). Leaves {matches, checksum_pair, checksum_rpay, checksum_spay, checksum_key, filtered}
+ * as six uint64 in d_out6 (device). Returns the number of kernels enqueued, < 0 on error. */
+int hwbrj_join_device_async(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args, void * d_out6);
+
 /* pinned host buffers for callers that want full-speed PCIe copies (bench e2e leg) */
 void * hwbrj_host_alloc(uint64_t bytes);
 void   hwbrj_host_free(void * p);

@@ -18,13 +18,13 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 from hwbloomradixjoin_b200 import BloomFilterArgs
-from hwbloomradixjoin_b200.dist import CudaOps, PeerFabric, dist_join, dist_join_peer
+from hwbloomradixjoin_b200.dist import CudaOps, PeerFabric, PeerJoinGraph, dist_join, dist_join_peer
 ops = CudaOps(dev)
 r, s, q = 2_000_000, 16_000_000, 0.01
 per_r, per_s = r // world, s // world
 R = ops.generate_shard(0, r, r, 1.0, 1, rank * per_r, r - rank * per_r if rank == world - 1 else per_r)
 S = ops.generate_shard(1, s, r, q, 2, rank * per_s, s - rank * per_s if rank == world - 1 else per_s)
-out, peer = [], []
+out, peer, graphed = [], [], []
 fabric = PeerFabric(ops, int(r / world * 1.25) + 65536, int(s / world * 1.25) + 65536)
 for case in [(0, 1 << 24, 1, 512), (0, 1 << 24, 3, 512), (1, 1 << 24, 4, 256), None]:
     bloom = BloomFilterArgs(*case) if case else None
@@ -33,6 +33,11 @@ for case in [(0, 1 << 24, 1, 512), (0, 1 << 24, 3, 512), (1, 1 << 24, 4, 256), N
     for rep in range(2):  # twice: the cursors must be reset correctly between joins
         pres = dist_join_peer(ops, fabric, R, S, bloom, r, s)
     peer.append({k: pres[k] for k in ("matches", "filtered", "checksum_pair", "checksum_key", "r_owned_total", "s_owned_total")})
+    pg = PeerJoinGraph(ops, fabric, R, S, bloom, r, s)  # the same pipeline captured as one CUDA graph
+    for rep in range(3):
+        gres = pg.replay()
+    graphed.append({k: gres[k] for k in ("matches", "filtered", "checksum_pair", "checksum_key", "r_owned_total", "s_owned_total")})
+    del pg
 # a receive buffer that is too small must be reported (None), never silently truncate
 small = PeerFabric(ops, 1000, 1000)
 overflowed = dist_join_peer(ops, small, R, S, None, r, s) is None
@@ -41,6 +46,7 @@ fabric.close()
 if rank == 0:
     print("RESULT " + json.dumps(out))
     print("PEER " + json.dumps(peer))
+    print("GRAPH " + json.dumps(graphed))
     print("OVERFLOW " + json.dumps(overflowed))
 dist.barrier()
 dist.destroy_process_group()
@@ -60,6 +66,8 @@ def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path):
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")][0]
     got = json.loads(line[7:])
     peer = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("PEER ")][0][5:])
+    graphed = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("GRAPH ")][0][6:])
+    assert graphed == peer
     assert json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("OVERFLOW ")][0][9:]) is True
     r, s, q = 2_000_000, 16_000_000, 0.01
     dR = Hgpu.DeviceRelation.generate(0, r, r, 1.0, 1)
