@@ -188,6 +188,9 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, args.workload, wl)
 
+    watchdog = threading.Timer(float(os.environ.get("HWBRJ_BENCH_WATCHDOG_S", "900")), lambda: os._exit(3))
+    watchdog.daemon = True  # a stuck run must not hold the GPU box
+    watchdog.start()
     rank, world, local = dist_env()
     if world > 1 or args.gpus > 1:
         from hwbloomradixjoin_b200 import bench_dist
@@ -243,6 +246,7 @@ def main():
                 "frac": achieved / peak, "traffic": ncu_traffic(f"{args.workload}:{'k_probe_compact' if bloom is not None else 'k_scatter'}"),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_set": dom_bytes, "ms_per_launch_set": dom_ms,
+                "note": "achieved = algorithmic bytes of the kernel's launches in one step / their summed CUDA-event time; traffic = ncu DRAM bytes of ONE launch",
                 "launches_per_step": stats[-1]["range_passes"] if bloom is not None else 1,
                 "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak}}
@@ -290,10 +294,13 @@ def main():
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only) ----
     cpu = None
     if not args.no_cpu_baseline:
-        nthreads = os.cpu_count() or 1
-        out = cpu_reference_sample(wl, args.ref_scale, nthreads, H, reps=1)
-        cpu = {"value": out["tuples"] / out["times"][0] / 1e6, "unit": UNIT, "cores": out["cores"], "kind": out["kind"],
-               "sample": out["sample"], "seconds": out["times"][0]}
+        try:
+            nthreads = os.cpu_count() or 1
+            out = cpu_reference_sample(wl, args.ref_scale, nthreads, H, reps=1)
+            cpu = {"value": out["tuples"] / out["times"][0] / 1e6, "unit": UNIT, "cores": out["cores"],
+                   "kind": out["kind"], "sample": out["sample"], "seconds": out["times"][0]}
+        except Exception as exc:  # the baseline is a reported side number: never lose the bench line over it
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {exc}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
