@@ -246,6 +246,7 @@ def main():
                 "frac": achieved / peak, "traffic": ncu_traffic(f"{args.workload}:{'k_probe_compact' if bloom is not None else 'k_scatter'}"),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_set": dom_bytes, "ms_per_launch_set": dom_ms,
+                "algorithmic_bytes_per_launch": dom_bytes // max(stats[-1]["range_passes"] if bloom is not None else 1, 1),
                 "note": "achieved = algorithmic bytes of the kernel's launches in one step / their summed CUDA-event time; traffic = ncu DRAM bytes of ONE launch",
                 "launches_per_step": stats[-1]["range_passes"] if bloom is not None else 1,
                 "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,

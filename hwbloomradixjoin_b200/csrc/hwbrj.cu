@@ -788,6 +788,7 @@ void hwbrj_rel_free(hwbrj_rel_t* rel) {
     delete rel;
 }
 hwbrj_rel_t* hwbrj_rel_wrap(void* device_tuples, uint64_t n) {
+    if (reinterpret_cast<uintptr_t>(device_tuples) & 15) return nullptr;  // the kernels stream 128-bit / TMA bulk loads
     hwbrj_rel_t* r = new hwbrj_rel;
     r->d = reinterpret_cast<uint2*>(device_tuples);
     r->n = n;
@@ -798,6 +799,7 @@ hwbrj_rel_t* hwbrj_rel_wrap(void* device_tuples, uint64_t n) {
 }
 hwbrj_rel_t* hwbrj_rel_wrap_counted(void* device_tuples, uint64_t capacity, const void* d_count, uint64_t expected) {
     hwbrj_rel_t* r = hwbrj_rel_wrap(device_tuples, capacity);
+    if (!r) return nullptr;
     r->n_dev = reinterpret_cast<const unsigned long long*>(d_count);
     r->n_expect = expected;
     return r;

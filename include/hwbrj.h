@@ -210,7 +210,9 @@ void hwbrj_set_stream(void * cuda_stream); /* run on the caller's stream (0 = th
 void hwbrj_reset_stream(void);             /* back to the library's own stream */
 int  hwbrj_sync(void);
 int  hwbrj_set_device(int device);           /* before the first call: one process per GPU */
-hwbrj_rel_t * hwbrj_rel_wrap(void * device_tuples, uint64_t n); /* non-owning view of device memory */
+/* non-owning view of device memory; the pointer must be 16-byte aligned (NULL otherwise); an odd tuple count makes the
+ * kernels read (not use) 8 bytes past the last tuple, which stay inside the allocation's last page */
+hwbrj_rel_t * hwbrj_rel_wrap(void * device_tuples, uint64_t n);
 /* same, but the real tuple count is a device-resident uint64 (written by an earlier kernel): `capacity` bounds it,
  * `expected` sizes the radix fan-out. Lets a pipeline run without host round trips. */
 hwbrj_rel_t * hwbrj_rel_wrap_counted(void * device_tuples, uint64_t capacity, const void * d_count, uint64_t expected);
