@@ -48,7 +48,12 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
 
     # exchanges fused into the partitioning kernels (NVLink peer stores); NCCL all-to-all is the fallback
     use_peer = os.environ.get("HWBRJ_DIST_PATH", "peer") == "peer"
-    fabric = PeerFabric(ops, int(r / world * 1.2) + 65536, int(s / world * 1.2) + 65536) if use_peer else None
+    fabric = None
+    if use_peer:
+        try:  # the constructor fails on ALL ranks together when peer memory cannot be mapped -> NCCL all-to-all path
+            fabric = PeerFabric(ops, int(r / world * 1.2) + 65536, int(s / world * 1.2) + 65536)
+        except Exception as exc:
+            print(f"[bench] NVLink peer path unavailable ({exc}); using NCCL all-to-all", flush=True)
 
     def step(Rt, St, time_phases=False):
         if fabric is not None:

@@ -275,10 +275,11 @@ class PeerFabric:
         if not all(self.local):
             raise RuntimeError("hwbrj_symm_alloc failed")
         handles = torch.zeros(3 * N_IPC, dtype=torch.uint8)
+        ok = 1
         for i, p in enumerate(self.local):
             buf = (C.c_ubyte * N_IPC)()
             if L.hwbrj_ipc_export(p, buf) != 0:
-                raise RuntimeError("cudaIpcGetMemHandle failed")
+                ok = 0  # keep going: the failure is agreed on collectively below, nobody is left waiting
             handles[i * N_IPC:(i + 1) * N_IPC] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
         handles = handles.to(ops.device)
         allh = [torch.empty_like(handles) for _ in range(self.world)]
@@ -292,11 +293,16 @@ class PeerFabric:
             ptrs = []
             for i in range(3):
                 raw = (C.c_ubyte * N_IPC).from_buffer_copy(hb[i * N_IPC:(i + 1) * N_IPC])
-                p = L.hwbrj_ipc_open(raw)
+                p = L.hwbrj_ipc_open(raw) if ok else None
                 if not p:
-                    raise RuntimeError(f"cudaIpcOpenMemHandle failed for rank {g}")
+                    ok = 0
                 ptrs.append(p)
             self.peer.append(ptrs)
+        # agree collectively: if any rank could not map a peer buffer, every rank gives up on the peer path together
+        flag = torch.tensor([ok], dtype=torch.int32, device=ops.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            raise RuntimeError("CUDA IPC peer mapping unavailable on at least one rank")
         self._bar = torch.zeros(1, dtype=torch.int32, device=ops.device)
         self.ctrl_view = ops.view_int64(self.local[2], self.CTRL_BYTES // 8)
         self.parity = 0
