@@ -80,7 +80,7 @@ struct Ctx {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[8];
     uint32_t* d_crc = nullptr;
-    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, ctrl, rt1, rp, sc, st1, inR, inS, scratch;
+    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, work_part, ctrl, rt1, rp, sc, st1, inR, inS, scratch;
     DevBuf cur1b, cur2b, tilesb;          // second set of scatter cursors: R partitioning may overlap the S probe
     cudaStream_t side_stream = nullptr;   // R partitioning runs here while K2 runs on the main stream
     cudaEvent_t ev_side[4];
@@ -137,10 +137,10 @@ static void init_ctx() {
     const int hist_smem = ((1 << kMaxRadixBits) + kCrcSmemWords) * 4;
     CK(cudaFuncSetAttribute(k_build_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    CK(cudaFuncSetAttribute(k_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
-    CK(cudaFuncSetAttribute(k_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
-    CK(cudaFuncSetAttribute(k_join<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
-    CK(cudaFuncSetAttribute(k_join<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableCap * (8 + 4 + 2)));
+    CK(cudaFuncSetAttribute(k_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
+    CK(cudaFuncSetAttribute(k_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
+    CK(cudaFuncSetAttribute(k_join<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
+    CK(cudaFuncSetAttribute(k_join<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
     if (const char* s = getenv("HWBRJ_RADIX_BITS")) g.radix_bits_override = atoi(s);
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
@@ -159,7 +159,7 @@ static void init_ctx() {
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter1, k_scatter<1>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter2, k_scatter<2>, kScatterThreads, kScatterSmem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join<false>, kJoinThreads, kTableCap * (8 + 4 + 2)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join<false>, kJoinThreads, kJoinSmemBytes));
     g.occ_scatter1 = std::max(g.occ_scatter1, 1);
     g.occ_scatter2 = std::max(g.occ_scatter2, 1);
     g.occ_join = std::max(g.occ_join, 1);
@@ -365,6 +365,7 @@ static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t
     g.cur2b.ensure(P * 4);
     g.tilesb.ensure((((size_t)1 << kMaxLevelBits) + 1) * 4);
     g.work.ensure((P + 1) * 4);
+    g.work_part.ensure((P + nS / kSChunk + 2) * 4);  // one entry per join work item
     g.ctrl.ensure(sizeof(Control));
     g.rt1.ensure(std::max<uint64_t>(nR, 1) * 8);
     g.rp.ensure(std::max<uint64_t>(nR, 1) * 8);
@@ -403,7 +404,9 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         if (!async_mode) CK(cudaEventRecord(e, s));
     };
     // nR/nS are exact counts, or capacities when the real counts live on the device (nR_dev/nS_dev)
-    if (nR >= (1ull << 32) || nS >= (1ull << 32)) die("relations of 2^32 or more tuples are not supported");
+    // 32-bit tuple indices; the slack keeps "index + one batch of loads" from wrapping in the kernels
+    if (nR >= (1ull << 32) - (1ull << 20) || nS >= (1ull << 32) - (1ull << 20))
+        die("relations of 2^32 - 2^20 or more tuples are not supported");
     if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
     if (args && nS_dev) die("device-side S count is only supported for the filter-less join");
     ensure_workspace(nR, nS, args);
@@ -515,15 +518,16 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
                                     g.st1.as<uint2>(), g.sc.as<uint2>(), launches, nullptr, false, pf);
     rec(g.ev[5], g.stream);
     if (overlap) CK(cudaStreamWaitEvent(g.stream, g.ev_side[1], 0));
-    k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>());
+    k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>(),
+                                         g.work_part.as<uint32_t>());
     launches++;
     if (pf.hash)
-        k_join<true><<<g.sms * g.occ_join, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
-            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
+        k_join<true><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
+            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), P, (uint32_t)bits,
             &ctrl->item_counter, &ctrl->acc);
     else
-        k_join<false><<<g.sms * g.occ_join, kJoinThreads, kTableCap * (8 + 4 + 2), g.stream>>>(
-            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), P, (uint32_t)bits,
+        k_join<false><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
+            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), P, (uint32_t)bits,
             &ctrl->item_counter, &ctrl->acc);
     launches++;
     g.last_Rp = Rp;
@@ -946,14 +950,14 @@ static int64_t materialize_last(uint2* d_pairs, uint64_t capacity) {
     CK(cudaMemsetAsync(&ctrl->acc, 0, sizeof(JoinAccum), g.stream));
     CK(cudaMemsetAsync(&ctrl->item_counter, 0, sizeof(uint32_t), g.stream));
     CK(cudaMemsetAsync(&ctrl->pair_cursor, 0, sizeof(unsigned long long), g.stream));
-    const int smem = kTableCap * (8 + 4 + 2);
+    const int smem = kJoinSmemBytes;
     if (g.last_hash)
         k_join<true, true><<<g.sms * g.occ_join, kJoinThreads, smem, g.stream>>>(
-            g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.last_P,
+            g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), g.last_P,
             g.last_bits, &ctrl->item_counter, &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
     else
         k_join<false, true><<<g.sms * g.occ_join, kJoinThreads, smem, g.stream>>>(
-            g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.last_P,
+            g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), g.last_P,
             g.last_bits, &ctrl->item_counter, &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->pair_cursor, 8, cudaMemcpyDeviceToHost, g.stream));

@@ -19,7 +19,7 @@ constexpr int kTableCap = 8192;                      // R tuples per shared-memo
 #define HWBRJ_JOIN_THREADS 512
 #endif
 #ifndef HWBRJ_JOIN_UNROLL
-#define HWBRJ_JOIN_UNROLL 4
+#define HWBRJ_JOIN_UNROLL 2
 #endif
 #ifndef HWBRJ_SCATTER_THREADS
 #define HWBRJ_SCATTER_THREADS 256
@@ -35,6 +35,7 @@ constexpr int kTableCap = 8192;                      // R tuples per shared-memo
 #endif
 constexpr int kJoinThreads = HWBRJ_JOIN_THREADS;
 constexpr int kSChunk = 32768;                       // S tuples per join work item
+constexpr uint32_t kBigItems = 128;                  // partitions with more work items are expanded cooperatively
 constexpr int kScatterThreads = HWBRJ_SCATTER_THREADS;
 constexpr int kScatterTile = HWBRJ_SCATTER_TILE;     // tuples per scatter tile
 constexpr int kScatterStages = HWBRJ_SCATTER_STAGES; // TMA bulk-load ring depth
@@ -371,18 +372,13 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
 // replaces the local prefix (:808-811) and the cross-thread offset computation (:819-837).
 // One CTA of 1024 threads; P <= 2^14. Produces fine_off[P+1], level-1 bucket cursors, level-2 cursors and the
 // tile schedule of the level-2 pass (tile_off[P1+1]).
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t P, uint32_t b2,
-                                              uint32_t* __restrict__ fine_off, uint32_t* __restrict__ cursor1,
-                                              uint32_t* __restrict__ cursor2, uint32_t* __restrict__ tile_off) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t s_tiles[(1 << kMaxLevelBits) + 1];
-    const uint32_t per = (P + 1023u) / 1024u;
-    const uint32_t lo = threadIdx.x * per;
-    uint32_t local = 0;
-    for (uint32_t i = 0; i < per; i++)
-        if (lo + i < P) local += hist[lo + i];
-    // block exclusive scan of `local`
-    uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+// Both single-CTA kernels below are pure latency: every thread fetches its (at most 16) bins with independent loads
+// in one round trip, keeps them in registers, and nothing is read back from global memory afterwards.
+constexpr int kBinsPerThread = (1 << kMaxRadixBits) / 1024;
+
+// exclusive block scan of one value per thread (1024 threads); returns the exclusive prefix, total via warp_sums[32]
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t local, uint32_t* warp_sums /* [33] */) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     uint32_t inc = local;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -400,34 +396,53 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist
             if (lane >= (uint32_t)d) winc += v;
         }
         warp_sums[lane] = winc - ws;
+        if (lane == 31) warp_sums[32] = winc;
     }
     __syncthreads();
-    uint32_t run = warp_sums[wid] + inc - local;
-    for (uint32_t i = 0; i < per; i++) {
-        uint32_t p = lo + i;
-        if (p < P) {
+    return warp_sums[wid] + inc - local;
+}
+
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t P, uint32_t b2,
+                                              uint32_t* __restrict__ fine_off, uint32_t* __restrict__ cursor1,
+                                              uint32_t* __restrict__ cursor2, uint32_t* __restrict__ tile_off) {
+    __shared__ uint32_t warp_sums[33];
+    __shared__ uint32_t s_l1[(1 << kMaxLevelBits) + 1];  // start offset of every level-1 bucket, then the total
+    const uint32_t per = (P + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per;
+    uint32_t v[kBinsPerThread];
+    uint32_t local = 0;
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; i++) {
+        v[i] = ((uint32_t)i < per && lo + i < P) ? hist[lo + i] : 0u;
+        local += v[i];
+    }
+    uint32_t run = block_exclusive_scan_1024(local, warp_sums);
+    const uint32_t submask = (1u << b2) - 1u;
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; i++) {
+        const uint32_t p = lo + i;
+        if ((uint32_t)i < per && p < P) {
             fine_off[p] = run;
             cursor2[p] = run;
-            if ((p & ((1u << b2) - 1u)) == 0u) cursor1[p >> b2] = run;
-            run += hist[p];
+            if ((p & submask) == 0u) {
+                cursor1[p >> b2] = run;
+                s_l1[p >> b2] = run;
+            }
+            run += v[i];
         }
     }
-    if (threadIdx.x == 1023) fine_off[P] = run;  // thread 1023 owns the tail (or nothing): run == total
-    __syncthreads();
-    __threadfence_block();
-    // level-2 tile schedule: tiles per level-1 bucket
     const uint32_t P1 = P >> b2;
     if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t j = 0; j < P1; j++) {
-            s_tiles[j] = acc;
-            uint32_t nb = fine_off[(j + 1) << b2] - fine_off[j << b2];
-            acc += (nb + kScatterTile - 1) / kScatterTile;
-        }
-        s_tiles[P1] = acc;
+        const uint32_t total = warp_sums[32];
+        fine_off[P] = total;
+        s_l1[P1] = total;
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j <= P1; j += blockDim.x) tile_off[j] = s_tiles[j];
+    // level-2 tile schedule: tiles per level-1 bucket (P1 <= 128), scanned by the same block scan
+    const uint32_t tiles =
+        threadIdx.x < P1 ? (s_l1[threadIdx.x + 1] - s_l1[threadIdx.x] + kScatterTile - 1) / kScatterTile : 0u;
+    const uint32_t tex = block_exclusive_scan_1024(tiles, warp_sums);
+    if (threadIdx.x <= P1) tile_off[threadIdx.x] = tex;  // thread P1 has tiles == 0: its prefix is the grand total
 }
 
 // ---- destination-bin functions of the scatter kernel -----------------------------------------------------------------
@@ -710,158 +725,218 @@ __global__ void __launch_bounds__(512) k_filter_from_parts(const uint2* __restri
 
 // ---- join work list: one item per (partition, S chunk) --------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_worklist(const uint32_t* __restrict__ r_off, const uint32_t* __restrict__ s_off,
-                                                  uint32_t P, uint32_t* __restrict__ work_off) {
-    // single CTA, serial-per-thread chunks + block scan (P <= 16384)
-    __shared__ uint32_t warp_sums[32];
+                                                  uint32_t P, uint32_t* __restrict__ work_off,
+                                                  uint32_t* __restrict__ work_part) {
+    // single CTA (P <= 16384). work_part[item] = partition of the item, so that the join kernel finds its partition
+    // with one load instead of a binary search over work_off.
+    __shared__ uint32_t warp_sums[33];
+    __shared__ uint32_t s_big[1024][3], s_nbig;  // partitions with many items are expanded by the whole CTA
+    if (threadIdx.x == 0) s_nbig = 0u;
     const uint32_t per = (P + 1023u) / 1024u;
     const uint32_t lo = threadIdx.x * per;
+    uint32_t items[kBinsPerThread];
     uint32_t local = 0;
-    for (uint32_t i = 0; i < per; i++) {
-        uint32_t p = lo + i;
-        if (p < P) {
-            uint32_t nr = r_off[p + 1] - r_off[p], ns = s_off[p + 1] - s_off[p];
-            local += (nr && ns) ? (ns + kSChunk - 1) / kSChunk : 0u;
-        }
-    }
-    uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    uint32_t inc = local;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= (uint32_t)d) inc += v;
-    }
-    if (lane == 31) warp_sums[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t ws = warp_sums[lane], winc = ws;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= (uint32_t)d) winc += v;
+    for (int i = 0; i < kBinsPerThread; i++) {
+        const uint32_t p = lo + i;
+        items[i] = 0u;
+        if ((uint32_t)i < per && p < P) {
+            const uint32_t nr = r_off[p + 1] - r_off[p], ns = s_off[p + 1] - s_off[p];
+            items[i] = (nr && ns) ? (ns + kSChunk - 1) / kSChunk : 0u;
         }
-        warp_sums[lane] = winc - ws;
+        local += items[i];
     }
-    __syncthreads();
-    uint32_t run = warp_sums[wid] + inc - local;
-    for (uint32_t i = 0; i < per; i++) {
-        uint32_t p = lo + i;
-        if (p < P) {
+    uint32_t run = block_exclusive_scan_1024(local, warp_sums);
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; i++) {
+        const uint32_t p = lo + i;
+        if ((uint32_t)i < per && p < P) {
             work_off[p] = run;
-            uint32_t nr = r_off[p + 1] - r_off[p], ns = s_off[p + 1] - s_off[p];
-            run += (nr && ns) ? (ns + kSChunk - 1) / kSChunk : 0u;
+            // > kBigItems chunks = > 4 M tuples: fewer than 2^32 / 2^22 = 1024 such partitions can exist
+            if (items[i] > kBigItems) {
+                const uint32_t slot = atomicAdd(&s_nbig, 1u);
+                s_big[slot][0] = p;
+                s_big[slot][1] = run;
+                s_big[slot][2] = items[i];
+            } else {
+                for (uint32_t c = 0; c < items[i]; c++) work_part[run + c] = p;
+            }
+            run += items[i];
         }
     }
-    if (threadIdx.x == 1023) work_off[P] = run;
+    if (threadIdx.x == 0) work_off[P] = warp_sums[32];
+    __syncthreads();
+    const uint32_t nbig = s_nbig;
+    for (uint32_t b = 0; b < nbig; b++) {
+        const uint32_t p = s_big[b][0], first = s_big[b][1], n_items = s_big[b][2];
+        for (uint32_t c = threadIdx.x; c < n_items; c += 1024u) work_part[first + c] = p;
+    }
 }
 
 // ---- K5: per-partition build + probe with the table in shared memory -----------------------------------------------
 // replaces bucket_chaining_join (:260-329): bucket heads + next links over the R partition held in shared
-// memory, idx = (key >> radix_bits) & (N-1) (HASH_BIT_MODULO with MASK=(N-1)<<bits), every equal key along the
-// chain counts. R partitions larger than kTableCap are processed in rounds; S partitions larger than kSChunk are
+// memory, idx = (key >> radix_bits) & (N-1) (HASH_BIT_MODULO with MASK=(N-1)<<bits), every equal key on the
+// chain counts. R partitions larger than kTableRound are processed in rounds; S partitions larger than kSChunk are
 // split over several work items (each rebuilds the table) so that skewed S does not serialise on one SM.
 // HASHPART: partitions come from the hash (filter-slice) partitioning, so the table index is key & (N-1).
 // PAIRS: materialise the output like -DJOIN_RESULT_MATERIALIZE does (:307-312): one {R.payload, S.payload} tuple per
 // match, appended to pairs_out through a warp-aggregated atomic cursor; pairs beyond pair_capacity are dropped (the
 // count stays exact, the caller retries with a larger buffer).
+//
+// The kernel is latency-bound (a partition is ~60 KB of R and ~60 KB of S), so the round trips are overlapped:
+//  * the R partition arrives as ONE TMA bulk copy straight into the table (cp.async.bulk -> mbarrier); the <= 2 tuples
+//    outside its 16-byte-aligned interior are loaded by two other threads;
+//  * while it is in flight, thread 0 claims the NEXT work item (atomic + one load of work_part), every thread clears
+//    its part of head[] and issues its first batch of S loads;
+//  * in the probe loop the next batch of S is requested before the current one is processed.
+// Tuple j of the round lives in slot j + off, off = parity of its global address / 8 (keeps the bulk copy aligned).
+constexpr uint32_t kTableRound = kTableCap - 2;  // tuples per round: leaves room for the alignment shift
+constexpr int kJoinSmemBytes = kTableCap * (8 + 4 + 2);
+
 template <bool HASHPART, bool PAIRS = false>
-__global__ void __launch_bounds__(kJoinThreads) k_join(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
+__global__ void __launch_bounds__(kJoinThreads, 2) k_join(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
                                                       const uint2* __restrict__ Sp, const uint32_t* __restrict__ s_off,
-                                                      const uint32_t* __restrict__ work_off, uint32_t P, uint32_t bits,
+                                                      const uint32_t* __restrict__ work_off,
+                                                      const uint32_t* __restrict__ work_part, uint32_t P, uint32_t bits,
                                                       uint32_t* __restrict__ item_counter, JoinAccum* __restrict__ acc_out,
                                                       uint2* __restrict__ pairs_out = nullptr,
                                                       unsigned long long* __restrict__ pair_cursor = nullptr,
                                                       unsigned long long pair_capacity = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2* tab = reinterpret_cast<uint2*>(smem_raw);                  // kTableCap tuples
-    uint32_t* head = reinterpret_cast<uint32_t*>(tab + kTableCap);    // kTableCap heads (index+1, 0 = empty)
+    uint2* tab = reinterpret_cast<uint2*>(smem_raw);                  // kTableCap slots
+    uint32_t* head = reinterpret_cast<uint32_t*>(tab + kTableCap);    // kTableCap heads (slot+1, 0 = empty)
     uint16_t* next = reinterpret_cast<uint16_t*>(head + kTableCap);   // kTableCap links
-    __shared__ uint32_t s_item, s_part;
+    __shared__ uint32_t s_item[2], s_part[2];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned long long s_red[5][kJoinThreads / 32];
     unsigned long long matches = 0, cpair = 0, crpay = 0, cspay = 0, ckey = 0;
     const uint32_t total = work_off[P];
     const uint64_t pol = policy_evict_first();
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {  // one thread fetches the next work item and locates its partition
-            const uint32_t it = atomicAdd(item_counter, 1u);
-            s_item = it;
-            if (it < total) {
-                uint32_t lo = 0, hi = P;
-                while (hi - lo > 1u) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (work_off[mid] <= it) lo = mid; else hi = mid;
-                }
-                s_part = lo;
-            }
+    constexpr int U = HWBRJ_JOIN_UNROLL;  // independent 8-byte S loads per thread and batch
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1u);
+        mbar_fence_init();
+        const uint32_t it = atomicAdd(item_counter, 1u);
+        s_item[0] = it;
+        if (it < total) s_part[0] = work_part[it];
+    }
+    auto emit = [&](uint32_t rpay, const uint2 s) {  // one output pair {R.payload, S.payload} (:303-315)
+        if (PAIRS) {
+            const uint32_t am = __activemask();
+            const uint32_t lane = threadIdx.x & 31u;
+            const int leader = __ffs(am) - 1;
+            unsigned long long pos = 0ull;
+            if ((int)lane == leader) pos = atomicAdd(pair_cursor, (unsigned long long)__popc(am));
+            pos = __shfl_sync(am, pos, leader) + __popc(am & ((1u << lane) - 1u));
+            if (pos < pair_capacity) pairs_out[pos] = make_uint2(rpay, s.y);
         }
-        __syncthreads();
-        const uint32_t item = s_item;
+        matches++;
+        cpair += mix64(rpay, s.y);
+        crpay += rpay;
+        cspay += s.y;
+        ckey += s.x;
+    };
+    uint32_t par = 0u, phase = 0u;
+    for (;; par ^= 1u) {
+        __syncthreads();  // previous item completely done: table free, s_item[par] visible
+        const uint32_t item = s_item[par];
         if (item >= total) break;
-        const uint32_t p = s_part;
+        const uint32_t p = s_part[par];
         const uint32_t chunk = item - work_off[p];
         const uint32_t r0 = r_off[p], nr = r_off[p + 1] - r0;
         const uint32_t sbeg = s_off[p] + chunk * kSChunk;
         const uint32_t send = min(s_off[p + 1], sbeg + (uint32_t)kSChunk);
-        for (uint32_t rb = 0; rb < nr; rb += kTableCap) {
-            const uint32_t cnt = min((uint32_t)kTableCap, nr - rb);
+        for (uint32_t rb = 0; rb < nr; rb += kTableRound) {
+            const uint32_t cnt = min(kTableRound, nr - rb);
             uint32_t N = 1u;
             while (N < cnt) N <<= 1;
             const uint32_t nmask = N - 1u;
-            if (rb) __syncthreads();
-            for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) head[i] = 0u;
-            __syncthreads();
-            constexpr int U = HWBRJ_JOIN_UNROLL;  // independent 8-byte loads in flight per thread
+            if (rb) __syncthreads();  // probe of the previous round done
             const uint2* Rbase = Rp + (uint64_t)r0 + rb;
-            for (uint32_t i0 = threadIdx.x; i0 < cnt; i0 += U * kJoinThreads) {
-                uint2 t[U];
+            const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(Rbase) >> 3) & 1u);
+            const uint32_t nbulk = (cnt - off) & ~1u;  // tuples [off, off + nbulk) are 16-byte aligned pairs (cnt >= 1)
+            uint32_t nxt = 0u;
+            if (threadIdx.x == 0) {
+                if (nbulk) {
+                    mbar_arrive_expect_tx(&s_bar, nbulk * 8u);
+                    bulk_g2s(tab + 2u * off, Rbase + off, nbulk * 8u, &s_bar);
+                }
+                if (rb == 0) nxt = atomicAdd(item_counter, 1u);  // next item: its latency hides under this one
+            } else if (threadIdx.x == 32) {
+                if (off) tab[1] = ld_stream_v2(Rbase, pol);
+            } else if (threadIdx.x == 64) {
+                if (off + nbulk < cnt) tab[cnt - 1u + off] = ld_stream_v2(Rbase + cnt - 1u, pol);
+            }
+            for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) head[i] = 0u;
+            // first batch of S: in flight during the build
+            uint32_t i0 = sbeg + threadIdx.x;
+            uint2 sv[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    uint32_t i = i0 + u * kJoinThreads;
-                    if (i < cnt) t[u] = ld_stream_v2(Rbase + i, pol);
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * kJoinThreads;
+                sv[u] = i < send ? ld_stream_v2(Sp + i, pol) : make_uint2(0u, 0u);
+            }
+            __syncthreads();  // head[] cleared, edge tuples stored
+            if (threadIdx.x == 0 && rb == 0) {
+                s_item[par ^ 1u] = nxt;  // read by the CTA after the barrier at the top of the next item
+                if (nxt < total) s_part[par ^ 1u] = work_part[nxt];
+            }
+            if (nbulk) {
+                mbar_wait(&s_bar, phase);
+                phase ^= 1u;
+            }
+            constexpr int UB = 4;  // build: independent table inserts per thread and step
+            for (uint32_t j0 = threadIdx.x; j0 < cnt; j0 += UB * kJoinThreads) {
+                uint32_t key[UB], old[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const uint32_t j = j0 + u * kJoinThreads;
+                    key[u] = j < cnt ? tab[j + off].x : 0u;
                 }
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    uint32_t i = i0 + u * kJoinThreads;
-                    if (i < cnt) {
-                        tab[i] = t[u];
-                        next[i] = (uint16_t)atomicExch(&head[(HASHPART ? t[u].x : (t[u].x >> bits)) & nmask], i + 1u);
-                    }
+                for (int u = 0; u < UB; u++) {
+                    const uint32_t j = j0 + u * kJoinThreads;
+                    if (j < cnt) old[u] = atomicExch(&head[(HASHPART ? key[u] : (key[u] >> bits)) & nmask], j + off + 1u);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const uint32_t j = j0 + u * kJoinThreads;
+                    if (j < cnt) next[j + off] = (uint16_t)old[u];
                 }
             }
-            __syncthreads();
-            for (uint32_t i0 = sbeg + threadIdx.x; i0 < send; i0 += U * kJoinThreads) {
-                uint2 sv[U];
+            __syncthreads();  // table complete
+            for (;;) {
+                const uint32_t i1 = i0 + U * kJoinThreads;
+                uint2 sn[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    uint32_t i = i0 + u * kJoinThreads;
-                    if (i < send) sv[u] = ld_stream_v2(Sp + i, pol);
+                    const uint32_t i = i1 + u * kJoinThreads;
+                    sn[u] = i < send ? ld_stream_v2(Sp + i, pol) : make_uint2(0u, 0u);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    uint32_t i = i0 + u * kJoinThreads;
-                    if (i < send) {
+                    if (i0 + u * kJoinThreads < send) {
                         const uint2 s = sv[u];
+                        // The chain walk only compares keys; the (expensive) bookkeeping of a match runs once per S
+                        // tuple after the walk, where the warp has reconverged. A second match of the same S tuple
+                        // (duplicate build keys) flushes the first one inside the loop.
+                        uint32_t m_rpay = 0u;
+                        bool have = false;
                         for (uint32_t hit = head[(HASHPART ? s.x : (s.x >> bits)) & nmask]; hit; hit = next[hit - 1u]) {
-                            uint2 r = tab[hit - 1u];
+                            const uint2 r = tab[hit - 1u];
                             if (r.x == s.x) {
-                                if (PAIRS) {
-                                    const uint32_t am = __activemask();
-                                    const uint32_t lane = threadIdx.x & 31u;
-                                    const int leader = __ffs(am) - 1;
-                                    unsigned long long pos = 0ull;
-                                    if ((int)lane == leader) pos = atomicAdd(pair_cursor, (unsigned long long)__popc(am));
-                                    pos = __shfl_sync(am, pos, leader) + __popc(am & ((1u << lane) - 1u));
-                                    if (pos < pair_capacity) pairs_out[pos] = make_uint2(r.y, s.y);
-                                }
-                                matches++;
-                                cpair += mix64(r.y, s.y);
-                                crpay += r.y;
-                                cspay += s.y;
-                                ckey += s.x;
+                                if (have) emit(m_rpay, s);
+                                m_rpay = r.y;
+                                have = true;
                             }
                         }
+                        if (have) emit(m_rpay, s);
                     }
                 }
+                if (i1 >= send) break;
+                i0 = i1;
+#pragma unroll
+                for (int u = 0; u < U; u++) sv[u] = sn[u];
             }
         }
     }
