@@ -41,7 +41,18 @@ constexpr int kScatterTile = HWBRJ_SCATTER_TILE;     // tuples per scatter tile
 constexpr int kScatterStages = HWBRJ_SCATTER_STAGES; // TMA bulk-load ring depth
 constexpr int kScatterStageTuples = kScatterTile + 2; // +1 misaligned head, +1 rounding to 16 bytes
 constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTile) * 8;
-constexpr int kProbeV = 4;                           // 128-bit loads in flight per lane in K2
+#ifndef HWBRJ_PROBE_V
+#define HWBRJ_PROBE_V 4
+#endif
+#ifndef HWBRJ_PROBE_PREFETCH
+#define HWBRJ_PROBE_PREFETCH 0
+#endif
+#ifdef HWBRJ_PROBE_MINBLOCKS
+#define HWBRJ_PROBE_BOUNDS __launch_bounds__(kProbeWarps * 32, HWBRJ_PROBE_MINBLOCKS)
+#else
+#define HWBRJ_PROBE_BOUNDS __launch_bounds__(kProbeWarps * 32)
+#endif
+constexpr int kProbeV = HWBRJ_PROBE_V;               // 128-bit loads in flight per lane in K2
 
 struct BloomParams {
     uint32_t* filter;      // m/32 words
@@ -274,7 +285,7 @@ struct WarpRing {
 // read from HBM once, later passes read only what is still undecided.
 __host__ __device__ constexpr int kProbeSmemPerWarp(int mode) { return (mode & 8) ? (256 + 512) * 8 : 512 * 8; }
 template <int MODE>
-__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2* __restrict__ S, uint64_t n_static,
+__global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, uint64_t n_static,
                                                                    const unsigned long long* __restrict__ n_ptr,
                                                                    BloomParams bp_in, const uint32_t* __restrict__ g_crc,
                                                                    uint2* __restrict__ out,
@@ -309,14 +320,23 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
     const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
     constexpr uint64_t kPerIter = 32ull * kProbeV;  // pairs per warp iteration
 
-    for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
-        const uint64_t p0 = it * kPerIter + lane;
-        uint4 t[kProbeV];
+    auto load_batch = [&](uint4 (&dst)[kProbeV], uint64_t it) {
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
-            uint64_t idx = p0 + (uint64_t)j * 32u;
-            t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
+            const uint64_t idx = it * kPerIter + lane + (uint64_t)j * 32u;
+            dst[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
         }
+    };
+#if HWBRJ_PROBE_PREFETCH
+    uint4 t[kProbeV];
+    if (warp_global * kPerIter < npairs) load_batch(t, warp_global);
+#endif
+    for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
+        const uint64_t p0 = it * kPerIter + lane;
+#if !HWBRJ_PROBE_PREFETCH
+        uint4 t[kProbeV];
+        load_batch(t, it);
+#endif
         uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
         bool act[2 * kProbeV], later[2 * kProbeV];
 #pragma unroll
@@ -334,6 +354,11 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
                 w[q] = act[q] ? ld_filter(bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
             }
         }
+#if HWBRJ_PROBE_PREFETCH
+        // the next batch of S is requested while this batch's probes are in flight (out-of-range indices load nothing)
+        uint4 tn[kProbeV];
+        load_batch(tn, it + nwarps);
+#endif
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
             bool fa = act[2 * j] && (bp.k == 0u || bloom_test_rest(bp, base[2 * j], h[2 * j], y[2 * j], w[2 * j]));
@@ -347,6 +372,10 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_compact(const uint2*
                 dfr.drain_if_full(defer_out, defer_cursor, pol, lane);
             }
         }
+#if HWBRJ_PROBE_PREFETCH
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) t[j] = tn[j];
+#endif
     }
     if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
     if (kDefer && dfr.count) dfr.drain(dfr.count, defer_out, defer_cursor, pol, lane);
