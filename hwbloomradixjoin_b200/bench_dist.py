@@ -82,13 +82,15 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
                 return out
         return step(Rsh, Ssh)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a few hundred ms before its first sample: spawn it before the warm-up
     for _ in range(max(args.warmup, 3)):
         res = resident_step()
-    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.begin()  # waits for the first sample, then opens the sampling window
     dist.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()

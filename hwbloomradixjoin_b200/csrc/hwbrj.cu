@@ -505,6 +505,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
         Sin = g.sc.as<uint2>();
         n_dev = &ctrl->survivors;
     }
+    rec(g.ev[4], g.stream);  // ms_probe = the K2 launches only
     // radix histogram of the tuples that go on to the join (survivors, or all of S without a filter)
     if (pf.hash)
         k_build_hist<false, true><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc,
@@ -512,7 +513,6 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     else
         k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
     launches++;
-    rec(g.ev[4], g.stream);
     // with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc
     const uint2* Sp = run_partition(Sin, nS, n_dev, bits, b2, g.histS.as<uint32_t>(), g.offS.as<uint32_t>(),
                                     g.st1.as<uint2>(), g.sc.as<uint2>(), launches, nullptr, false, pf);

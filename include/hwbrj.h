@@ -116,8 +116,8 @@ typedef struct hwbrj_stats_t {
     float    ms_memset;     /* zero-fill of the filter and scratch (excluded from ms_total, as :1583 is) */
     float    ms_build;      /* R: Bloom insert + histogram */
     float    ms_part_r;     /* R: scatter passes */
-    float    ms_probe;      /* S: Bloom probe + compaction + histogram */
-    float    ms_part_s;     /* S: scatter passes */
+    float    ms_probe;      /* S: Bloom probe + compaction (the K2 launches) */
+    float    ms_part_s;     /* S: histogram + scan + scatter passes */
     float    ms_join;       /* per-partition build + probe */
     float    ms_h2d;        /* host->device copies (host-buffer entry points only) */
     float    ms_e2e;        /* wall clock of the whole host-buffer call, incl. copies */
