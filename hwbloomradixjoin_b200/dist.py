@@ -272,13 +272,11 @@ class PeerFabric:
         L = ops.L
         self.local = [L.hwbrj_symm_alloc((self.cap_r + 8) * 8), L.hwbrj_symm_alloc((self.cap_s + 8) * 8),
                       L.hwbrj_symm_alloc(self.CTRL_BYTES)]
-        if not all(self.local):
-            raise RuntimeError("hwbrj_symm_alloc failed")
         handles = torch.zeros(3 * N_IPC, dtype=torch.uint8)
-        ok = 1
+        ok = 1 if all(self.local) else 0  # a failed allocation is reported through the collective flag below as well
         for i, p in enumerate(self.local):
             buf = (C.c_ubyte * N_IPC)()
-            if L.hwbrj_ipc_export(p, buf) != 0:
+            if not ok or L.hwbrj_ipc_export(p, buf) != 0:
                 ok = 0  # keep going: the failure is agreed on collectively below, nobody is left waiting
             handles[i * N_IPC:(i + 1) * N_IPC] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
         handles = handles.to(ops.device)
