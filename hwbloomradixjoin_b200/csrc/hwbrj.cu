@@ -102,6 +102,7 @@ struct Ctx {
     int radix_bits_override = 0;
     int range_passes_override = 0;
     int probe_ctas_per_sm = 0;  // 0 = occupancy API
+    int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
     bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
     DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
     int occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
@@ -145,6 +146,7 @@ static void init_ctx() {
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
+    if (const char* s = getenv("HWBRJ_PROBE_CARVEOUT")) g.probe_carveout = std::min(100, atoi(s));
     if (const char* s = getenv("HWBRJ_DEFER")) g.defer_ranges = atoi(s) != 0;
     CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
@@ -251,6 +253,9 @@ static void launch_probe_mode(int mode, const uint2* in, uint64_t n, const unsig
             CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[M], k_probe_compact<M>, kProbeWarps * 32, smem)); \
             occ[M] = std::max(occ[M], 1);                                                                           \
+            if (g.probe_carveout >= 0)                                                                              \
+                CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
+                                        g.probe_carveout));                                                         \
         }                                                                                                           \
         /* measured on B200: 4 CTAs/SM beats the occupancy maximum (less L2 thrash of the filter range) */          \
         const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(occ[M], 4));                 \

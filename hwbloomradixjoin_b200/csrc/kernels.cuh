@@ -154,7 +154,24 @@ __device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t bas
     }
 }
 
-__device__ __forceinline__ uint32_t ld_filter(const uint32_t* p) { return __ldg(p); }
+// filter probe load: ld.global.cg (L2 only). Measured in K2 at C1: __ldg 5.2 ms, L1::no_allocate 9.5 ms, .cg 4.96 ms.
+// (K2 also slows down 3x when the L1 carve-out is minimal -- the in-flight loads of any flavour need L1 data space.)
+#ifndef HWBRJ_PROBE_LD
+#define HWBRJ_PROBE_LD 2
+#endif
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t* p) {
+#if HWBRJ_PROBE_LD == 1
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif HWBRJ_PROBE_LD == 2
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 
 // probes 1..k-1 (the first word is passed in so that callers can batch the first probes)
 __device__ __forceinline__ bool bloom_test_rest(const BloomParams& bp, uint32_t base, uint32_t h, uint32_t y,
@@ -283,7 +300,12 @@ struct WarpRing {
 // Range passes with deferral: pass i probes the keys whose first filter bit lies in range i (that part of the filter
 // stays L2-resident) and appends the keys of later ranges to `defer_out`, which is the next pass's input -- S is
 // read from HBM once, later passes read only what is still undecided.
-__host__ __device__ constexpr int kProbeSmemPerWarp(int mode) { return (mode & 8) ? (256 + 512) * 8 : 512 * 8; }
+#ifndef HWBRJ_PROBE_RING
+#define HWBRJ_PROBE_RING 512  // survivor ring per warp (tuples, power of two >= 128)
+#endif
+__host__ __device__ constexpr int kProbeSmemPerWarp(int mode) {
+    return (mode & 8) ? (256 + 512) * 8 : HWBRJ_PROBE_RING * 8;
+}
 template <int MODE>
 __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, uint64_t n_static,
                                                                    const unsigned long long* __restrict__ n_ptr,
@@ -294,7 +316,8 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
                                                                    unsigned long long* __restrict__ defer_cursor) {
     constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0,
                    kDefer = (MODE & 8) != 0;
-    constexpr int kSurvCap = kDefer ? 256 : 512;
+    constexpr int kSurvCap = kDefer ? 256 : HWBRJ_PROBE_RING;
+    static_assert(kSurvCap >= 128, "append2 adds up to 64 tuples between two drain checks");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
     BloomParams bp = bp_in;
