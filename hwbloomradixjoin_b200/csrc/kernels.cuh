@@ -47,6 +47,9 @@ constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTil
 #ifndef HWBRJ_PROBE_PREFETCH
 #define HWBRJ_PROBE_PREFETCH 0
 #endif
+#ifndef HWBRJ_PROBE_CLAIM_AHEAD
+#define HWBRJ_PROBE_CLAIM_AHEAD 0  // round-2 experiment: see WarpRing::claim_if_full
+#endif
 #ifdef HWBRJ_PROBE_MINBLOCKS
 #define HWBRJ_PROBE_BOUNDS __launch_bounds__(kProbeWarps * 32, HWBRJ_PROBE_MINBLOCKS)
 #else
@@ -269,7 +272,7 @@ template <int CAP>  // power of two; drained CAP/2 tuples at a time
 struct WarpRing {
     uint2* buf;
     uint32_t head, count;  // warp-uniform
-    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; }
+    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; pend_base = 0ull; pending = false; }
     __device__ __forceinline__ void append2(bool fa, uint2 a, bool fb, uint2 b, uint32_t lt) {
         const uint32_t ma = __ballot_sync(0xffffffffu, fa);
         const uint32_t mb = __ballot_sync(0xffffffffu, fb);
@@ -287,6 +290,29 @@ struct WarpRing {
         for (uint32_t i = lane; i < cnt; i += 32u) st_stream_v2(out + gb + i, buf[(head + i) & (CAP - 1)], pol);
         head = (head + cnt) & (CAP - 1);
         count -= cnt;
+        __syncwarp();
+    }
+    // ---- claim-ahead drains (HWBRJ_PROBE_CLAIM_AHEAD, untested on hardware yet): the output space of a drain is
+    // claimed at the end of one iteration and written at the start of the next, after that iteration's loads have
+    // been issued, so the round trip of the atomic on the shared cursor is hidden. Capacity: fewer than CAP/2 tuples
+    // are left after complete(), one iteration appends at most CAP/2.
+    unsigned long long pend_base;  // valid in lane 0 while pending
+    bool pending;                  // warp-uniform
+    __device__ __forceinline__ void claim_if_full(unsigned long long* cursor, uint32_t lane) {
+        if (!pending && count >= (uint32_t)(CAP / 2)) {
+            if (lane == 0) pend_base = atomicAdd(cursor, (unsigned long long)(CAP / 2));  // result consumed in complete()
+            pending = true;
+        }
+    }
+    __device__ __forceinline__ void complete(uint2* __restrict__ out, uint64_t pol, uint32_t lane) {
+        if (!pending) return;
+        __syncwarp();
+        const unsigned long long gb = __shfl_sync(0xffffffffu, pend_base, 0);
+        for (uint32_t i = lane; i < (uint32_t)(CAP / 2); i += 32u)
+            st_stream_v2(out + gb + i, buf[(head + i) & (CAP - 1)], pol);
+        head = (head + CAP / 2) & (CAP - 1);
+        count -= CAP / 2;
+        pending = false;
         __syncwarp();
     }
     // at most 64 tuples are appended between two calls, so one drain of CAP/2 keeps the ring from overflowing
@@ -382,6 +408,9 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
         uint4 tn[kProbeV];
         load_batch(tn, it + nwarps);
 #endif
+#if HWBRJ_PROBE_CLAIM_AHEAD
+        if (!kDefer) surv.complete(out, pol, lane);  // the claim was issued an iteration ago: its result is here by now
+#endif
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
             bool fa = act[2 * j] && (bp.k == 0u || bloom_test_rest(bp, base[2 * j], h[2 * j], y[2 * j], w[2 * j]));
@@ -389,17 +418,27 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
                       (bp.k == 0u || bloom_test_rest(bp, base[2 * j + 1], h[2 * j + 1], y[2 * j + 1], w[2 * j + 1]));
             const uint2 ta = make_uint2(t[j].x, t[j].y), tb = make_uint2(t[j].z, t[j].w);
             surv.append2(fa, ta, fb, tb, lt);
+#if HWBRJ_PROBE_CLAIM_AHEAD
+            if (kDefer) surv.drain_if_full(out, out_cursor, pol, lane);
+#else
             surv.drain_if_full(out, out_cursor, pol, lane);
+#endif
             if (kDefer) {
                 dfr.append2(later[2 * j], ta, later[2 * j + 1], tb, lt);
                 dfr.drain_if_full(defer_out, defer_cursor, pol, lane);
             }
         }
+#if HWBRJ_PROBE_CLAIM_AHEAD
+        if (!kDefer) surv.claim_if_full(out_cursor, lane);
+#endif
 #if HWBRJ_PROBE_PREFETCH
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) t[j] = tn[j];
 #endif
     }
+#if HWBRJ_PROBE_CLAIM_AHEAD
+    if (!kDefer) surv.complete(out, pol, lane);
+#endif
     if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
     if (kDefer && dfr.count) dfr.drain(dfr.count, defer_out, defer_cursor, pol, lane);
     // odd tail tuple
