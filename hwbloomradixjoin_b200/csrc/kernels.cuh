@@ -157,17 +157,21 @@ __device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t bas
     }
 }
 
-// filter probe load: ld.global.cg (L2 only). Measured in K2 at C1: __ldg 5.2 ms, L1::no_allocate 9.5 ms, .cg 4.96 ms.
+// filter probe load. BASIC: ld.global.cg (L2 only) -- measured in K2 at C1: __ldg 5.2 ms, L1::no_allocate 9.5 ms,
+// .cg 4.96 ms. BLOCKED keeps the L1-allocating __ldg: probes 2..k of a key fall into the block (often the very sector)
+// that its first probe has just brought into L1. HWBRJ_PROBE_LD forces one flavour for experiments (0 = __ldg,
+// 1 = nc.L1::no_allocate, 2 = .cg, 3 = by filter variant).
 // (K2 also slows down 3x when the L1 carve-out is minimal -- the in-flight loads of any flavour need L1 data space.)
 #ifndef HWBRJ_PROBE_LD
-#define HWBRJ_PROBE_LD 2
+#define HWBRJ_PROBE_LD 3
 #endif
-__device__ __forceinline__ uint32_t ld_filter(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_filter(const BloomParams& bp, const uint32_t* p) {
 #if HWBRJ_PROBE_LD == 1
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
-#elif HWBRJ_PROBE_LD == 2
+#elif HWBRJ_PROBE_LD == 2 || HWBRJ_PROBE_LD == 3
+    if (HWBRJ_PROBE_LD == 3 && bp.blocked) return __ldg(p);  // compile-time constant inside K2 (MODE bit 0)
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
@@ -185,7 +189,7 @@ __device__ __forceinline__ bool bloom_test_rest(const BloomParams& bp, uint32_t 
         h = (h + y) & bp.size_mask;
         y = (y + i) & bp.size_mask;
         a = base + h;
-        if (!((ld_filter(bp.filter + (a >> 5)) >> (a & 31u)) & 1u)) return false;
+        if (!((ld_filter(bp, bp.filter + (a >> 5)) >> (a & 31u)) & 1u)) return false;
     }
     return true;
 }
@@ -400,7 +404,7 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
                 bool mine = bloom_in_range(bp, a);
                 act[q] = valid && mine;
                 later[q] = kDefer && valid && !mine;  // inputs of pass i only hold ranges >= i
-                w[q] = act[q] ? ld_filter(bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
+                w[q] = act[q] ? ld_filter(bp, bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
             }
         }
 #if HWBRJ_PROBE_PREFETCH
@@ -448,7 +452,7 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
         bloom_start(bp, crc_tab, tt.x, b0, h0, y0);
         uint32_t a = b0 + h0;
         if (bloom_in_range(bp, a)) {
-            if (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp.filter + (a >> 5)))) {
+            if (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp, bp.filter + (a >> 5)))) {
                 unsigned long long pos = atomicAdd(out_cursor, 1ull);
                 out[pos] = tt;
             }
