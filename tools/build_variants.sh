@@ -1,0 +1,35 @@
+#!/bin/bash
+# development helper: compile tuning variants of the library into build/variants/ (run here, they travel with gpurun);
+# then `bash tools/sweep_variants.sh <workload>` on the GPU box times each one. One "name|nvcc -D flags" per line.
+set -e
+cd "$(dirname "$0")/.."
+mkdir -p build/variants
+F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared"
+SRC=hwbloomradixjoin_b200/csrc/hwbrj.cu
+spec=${1:-k2}
+case $spec in
+k2) list='
+a_base|
+b_claim_m4|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_MINBLOCKS=4
+c_claim_ring256_m4|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=256 -DHWBRJ_PROBE_MINBLOCKS=4
+d_claim_ring128_m4|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128 -DHWBRJ_PROBE_MINBLOCKS=4
+e_claim_ring128_m5_c5|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128 -DHWBRJ_PROBE_MINBLOCKS=5
+f_ld_cg_all|-DHWBRJ_PROBE_LD=2
+g_ld_ldg_all|-DHWBRJ_PROBE_LD=0
+' ;;
+join) list='
+a_base|
+b_join_u4|-DHWBRJ_JOIN_UNROLL=4
+c_join_u1|-DHWBRJ_JOIN_UNROLL=1
+' ;;
+*) echo "unknown spec $spec"; exit 1 ;;
+esac
+rm -f build/variants/lib_*.so
+while IFS='|' read -r name flags; do
+  [ -z "$name" ] && continue
+  nvcc $F $flags -o build/variants/lib_$name.so $SRC -ldl &
+done <<< "$list"
+wait
+for f in build/variants/lib_*.so; do
+  echo "$(basename $f) $(cuobjdump --dump-resource-usage $f | grep -A1 'k_probe_compactILi6E' | grep -o 'REG:[0-9]* STACK:[0-9]*')"
+done
