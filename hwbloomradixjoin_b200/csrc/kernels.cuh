@@ -47,6 +47,9 @@ constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTil
 #ifndef HWBRJ_PROBE_PREFETCH
 #define HWBRJ_PROBE_PREFETCH 0
 #endif
+#ifndef HWBRJ_K2_ABLATE
+#define HWBRJ_K2_ABLATE 0  // TIMING EXPERIMENTS ONLY (results are wrong): 1 = no filter loads, 2 = no shared output cursor
+#endif
 #ifndef HWBRJ_PROBE_CLAIM_AHEAD
 #define HWBRJ_PROBE_CLAIM_AHEAD 0  // round-2 experiment: see WarpRing::claim_if_full
 #endif
@@ -276,7 +279,7 @@ template <int CAP>  // power of two; drained CAP/2 tuples at a time
 struct WarpRing {
     uint2* buf;
     uint32_t head, count;  // warp-uniform
-    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; pend_base = 0ull; pending = false; }
+    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; pend_base = 0ull; pending = false; priv_next = 0ull; }
     __device__ __forceinline__ void append2(bool fa, uint2 a, bool fb, uint2 b, uint32_t lt) {
         const uint32_t ma = __ballot_sync(0xffffffffu, fa);
         const uint32_t mb = __ballot_sync(0xffffffffu, fb);
@@ -289,8 +292,13 @@ struct WarpRing {
                                           uint32_t lane) {
         __syncwarp();
         unsigned long long gb = 0ull;
+#if HWBRJ_K2_ABLATE & 2
+        gb = priv_next;  // private output region of this warp: measures K2 without the atomic on the shared cursor
+        priv_next += cnt;
+#else
         if (lane == 0) gb = atomicAdd(cursor, (unsigned long long)cnt);
         gb = __shfl_sync(0xffffffffu, gb, 0);
+#endif
         for (uint32_t i = lane; i < cnt; i += 32u) st_stream_v2(out + gb + i, buf[(head + i) & (CAP - 1)], pol);
         head = (head + cnt) & (CAP - 1);
         count -= cnt;
@@ -300,6 +308,7 @@ struct WarpRing {
     // claimed at the end of one iteration and written at the start of the next, after that iteration's loads have
     // been issued, so the round trip of the atomic on the shared cursor is hidden. Capacity: fewer than CAP/2 tuples
     // are left after complete(), one iteration appends at most CAP/2.
+    unsigned long long priv_next;  // HWBRJ_K2_ABLATE & 2 only
     unsigned long long pend_base;  // valid in lane 0 while pending
     bool pending;                  // warp-uniform
     __device__ __forceinline__ void claim_if_full(unsigned long long* cursor, uint32_t lane) {
@@ -372,6 +381,9 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
     const uint64_t warp_global = (uint64_t)blockIdx.x * kProbeWarps + wid;
     const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
     constexpr uint64_t kPerIter = 32ull * kProbeV;  // pairs per warp iteration
+#if HWBRJ_K2_ABLATE & 2
+    surv.priv_next = warp_global * (n / nwarps);
+#endif
 
     auto load_batch = [&](uint4 (&dst)[kProbeV], uint64_t it) {
 #pragma unroll
@@ -404,7 +416,11 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
                 bool mine = bloom_in_range(bp, a);
                 act[q] = valid && mine;
                 later[q] = kDefer && valid && !mine;  // inputs of pass i only hold ranges >= i
+#if HWBRJ_K2_ABLATE & 1
+                w[q] = 0u;  // no filter traffic: what is left is the S stream, the hashing and the range test
+#else
                 w[q] = act[q] ? ld_filter(bp, bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
+#endif
             }
         }
 #if HWBRJ_PROBE_PREFETCH

@@ -17,6 +17,12 @@ e_claim_ring128_m5_c5|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128 -DHWBRJ
 f_ld_cg_all|-DHWBRJ_PROBE_LD=2
 g_ld_ldg_all|-DHWBRJ_PROBE_LD=0
 ' ;;
+ablate) list='
+a_base|
+b_no_filter_loads|-DHWBRJ_K2_ABLATE=1
+c_no_shared_cursor|-DHWBRJ_K2_ABLATE=2
+d_stream_hash_only|-DHWBRJ_K2_ABLATE=3
+' ;;
 join) list='
 a_base|
 b_join_u4|-DHWBRJ_JOIN_UNROLL=4
