@@ -103,6 +103,7 @@ struct Ctx {
     int range_passes_override = 0;
     int probe_ctas_per_sm = 0;  // 0 = occupancy API
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
+    bool probe_staged = false;  // experimental: k >= 2 probes run on compacted candidates (k_probe_staged)
     bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
     DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
     int occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
@@ -147,6 +148,7 @@ static void init_ctx() {
     if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_CARVEOUT")) g.probe_carveout = std::min(100, atoi(s));
+    if (const char* s = getenv("HWBRJ_PROBE_STAGED")) g.probe_staged = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_DEFER")) g.defer_ranges = atoi(s) != 0;
     CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
@@ -262,6 +264,25 @@ static void launch_probe_mode(int mode, const uint2* in, uint64_t n, const unsig
         k_probe_compact<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor,     \
                                                                        defer_out, defer_cursor);                    \
         break;                                                                                                      \
+    }
+    if (g.probe_staged && bp.k >= 2u && !(mode & (2 | 8))) {  // experimental staged probe for k >= 2 (HWBRJ_PROBE_STAGED=1)
+        const int smem = kProbeWarps * kProbeSmemPerWarp(0);
+        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : 4);
+#define HWBRJ_STAGED_CASE(M)                                                                                        \
+    case M: {                                                                                                       \
+        static bool attr = false;                                                                                   \
+        if (!attr) {                                                                                                \
+            CK(cudaFuncSetAttribute(k_probe_staged<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
+            attr = true;                                                                                            \
+        }                                                                                                           \
+        k_probe_staged<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor);      \
+        return;                                                                                                     \
+    }
+        switch (mode) {
+            HWBRJ_STAGED_CASE(0) HWBRJ_STAGED_CASE(1) HWBRJ_STAGED_CASE(4) HWBRJ_STAGED_CASE(5)
+            default: break;
+        }
+#undef HWBRJ_STAGED_CASE
     }
     switch (mode) {
         HWBRJ_PROBE_CASE(0) HWBRJ_PROBE_CASE(1) HWBRJ_PROBE_CASE(2) HWBRJ_PROBE_CASE(3)

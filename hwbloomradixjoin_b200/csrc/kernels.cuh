@@ -288,6 +288,11 @@ struct WarpRing {
         if (fb) buf[(tail + __popc(ma) + __popc(mb & lt)) & (CAP - 1)] = b;
         count += __popc(ma) + __popc(mb);
     }
+    __device__ __forceinline__ void append1(bool f, uint2 a, uint32_t lt) {
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (f) buf[(head + count + __popc(m & lt)) & (CAP - 1)] = a;
+        count += __popc(m);
+    }
     __device__ __forceinline__ void drain(uint32_t cnt, uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol,
                                           uint32_t lane) {
         __syncwarp();
@@ -475,6 +480,111 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
         } else if (kDefer) {
             unsigned long long pos = atomicAdd(defer_cursor, 1ull);
             defer_out[pos] = tt;
+        }
+    }
+}
+
+// ---- K2 for k >= 2, staged (experimental, HWBRJ_PROBE_STAGED=1; not validated on hardware yet) ------------------------
+// With several probes per key the plain kernel walks probes 2..k under divergence: after the first probe 38 % of the
+// lanes are still alive at C1-blocked (k = 4), then 14 %, then 5 %, but the warp pays for every round. Here the keys that
+// pass their FIRST probe are compacted into a per-warp candidate ring (the tuple only), and probes 2..k run on full
+// batches of 32 candidates, one per lane, re-deriving the index sequence from the key; a batch stops as soon as no
+// lane is alive. Survivors go to a second, smaller ring (few tuples survive k probes).
+template <int MODE>  // bit0 BLOCKED, bit2 ranged
+__global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* __restrict__ S, uint64_t n_static,
+                                                                  const unsigned long long* __restrict__ n_ptr,
+                                                                  BloomParams bp_in, const uint32_t* __restrict__ g_crc,
+                                                                  uint2* __restrict__ out,
+                                                                  unsigned long long* __restrict__ out_cursor) {
+    constexpr bool kBlocked = (MODE & 1) != 0, kRanged = (MODE & 4) != 0;
+    constexpr int kCandCap = 256, kSurvCap = 256;
+    static_assert((kCandCap + kSurvCap) * 8 == kProbeSmemPerWarp(0) || HWBRJ_PROBE_RING != 512, "smem per warp");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
+    BloomParams bp = bp_in;
+    bp.blocked = kBlocked ? 1u : 0u;
+    if (!kRanged) bp.nranges = 1u;
+    if (kBlocked) {
+        load_crc_tab(crc_tab, g_crc);
+        __syncthreads();
+    }
+    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2* wsm = reinterpret_cast<uint2*>(smem_raw) + wid * (kCandCap + kSurvCap);
+    WarpRing<kCandCap> cand;
+    cand.init(wsm);
+    WarpRing<kSurvCap> surv;
+    surv.init(wsm + kCandCap);
+    const uint64_t pol = policy_evict_first();
+    const uint64_t npairs = n >> 1;
+    const uint4* S4 = reinterpret_cast<const uint4*>(S);
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kProbeWarps + wid;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
+    constexpr uint64_t kPerIter = 32ull * kProbeV;
+
+    // probes 2..k of up to 32 candidates (one per lane); the survivors move to the output ring
+    auto finish_batch = [&](uint32_t nb) {
+        __syncwarp();  // the candidates were stored by other lanes
+        const uint2 tt = cand.buf[(cand.head + lane) & (kCandCap - 1)];
+        cand.head = (cand.head + nb) & (kCandCap - 1);
+        cand.count -= nb;
+        uint32_t base, h, y;
+        bloom_start(bp, crc_tab, tt.x, base, h, y);
+        bool alive = lane < nb;
+        for (uint32_t i = 1; i < bp.k; i++) {
+            if (!__any_sync(0xffffffffu, alive)) break;
+            h = (h + y) & bp.size_mask;
+            y = (y + i) & bp.size_mask;
+            const uint32_t a = base + h;
+            if (alive) alive = ((ld_filter(bp, bp.filter + (a >> 5)) >> (a & 31u)) & 1u) != 0u;
+        }
+        surv.append1(alive, tt, lt);
+        surv.drain_if_full(out, out_cursor, pol, lane);
+        __syncwarp();  // all lanes have read their candidate before the ring is appended to again
+    };
+
+    for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
+        const uint64_t p0 = it * kPerIter + lane;
+        uint4 t[kProbeV];
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            const uint64_t idx = p0 + (uint64_t)j * 32u;
+            t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t a0[2 * kProbeV], w[2 * kProbeV];
+        bool act[2 * kProbeV];
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            const bool valid = (p0 + (uint64_t)j * 32u) < npairs;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int q = 2 * j + e;
+                uint32_t base, h, y;
+                bloom_start(bp, crc_tab, e ? t[j].z : t[j].x, base, h, y);
+                a0[q] = base + h;
+                act[q] = valid && bloom_in_range(bp, a0[q]);
+                w[q] = act[q] ? ld_filter(bp, bp.filter + (a0[q] >> 5)) : 0u;  // all first probes in flight together
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            const bool fa = act[2 * j] && ((w[2 * j] >> (a0[2 * j] & 31u)) & 1u);
+            const bool fb = act[2 * j + 1] && ((w[2 * j + 1] >> (a0[2 * j + 1] & 31u)) & 1u);
+            cand.append2(fa, make_uint2(t[j].x, t[j].y), fb, make_uint2(t[j].z, t[j].w), lt);
+            while (cand.count >= 32u) finish_batch(32u);  // leaves < 32, at most 64 are appended per step: never full
+        }
+    }
+    if (cand.count) finish_batch(cand.count);
+    if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
+    if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail tuple
+        const uint2 tt = S[n - 1];
+        uint32_t b0, h0, y0;
+        bloom_start(bp, crc_tab, tt.x, b0, h0, y0);
+        const uint32_t a = b0 + h0;
+        if (bloom_in_range(bp, a) && bloom_test_rest(bp, b0, h0, y0, ld_filter(bp, bp.filter + (a >> 5)))) {
+            const unsigned long long pos = atomicAdd(out_cursor, 1ull);
+            out[pos] = tt;
         }
     }
 }
