@@ -86,8 +86,8 @@ result_t * BPRH(relation_t * relR, relation_t * relS, int nthreads, bloom_filter
 result_t * BPRHO(relation_t * relR, relation_t * relS, int nthreads, bloom_filter_args_t * args); /* :1799 */
 result_t * PRO(relation_t * relR, relation_t * relS, int nthreads);                               /* parallel_radix_join.c:1697 */
 result_t * RJ(relation_t * relR, relation_t * relS, int nthreads);                                /* :1718 */
-result_t * PRH(relation_t * relR, relation_t * relS, int nthreads);
-result_t * PRHO(relation_t * relR, relation_t * relS, int nthreads);
+result_t * PRH(relation_t * relR, relation_t * relS, int nthreads);                               /* :1704 */
+result_t * PRHO(relation_t * relR, relation_t * relS, int nthreads);                              /* :1711 */
 
 /* ------------------------------------------------------------------------------------------- */
 /* Part 2: extensions                                                                           */
