@@ -38,7 +38,15 @@ WORKLOADS = {
                    "canonical inputs, -b blocked -B 256 -k 4"),
     "c3": (128_000_000, 128_000_000, 1.0, None, 0, 0, 0, "Workload B plain PRO: -r 128000000 -s 128000000"),
     "small": (1_000_000, 8_000_000, 0.01, 0, 1 << 23, 1, 512, "1M x 8M smoke-sized"),
+    # q < 0 means: S holds Zipf-distributed foreign keys with exponent -q (mchashjoins -z, create_relation_zipf)
+    "c5_zipf": (128_000_000, 1_024_000_000, -1.0, 0, 1 << 30, 1, 512,
+                "Zipf-skewed S: -r 128000000 -s 1024000000 -z 1.0 -b basic -m 1073741824 -k 1"),
 }
+
+
+def s_generator(q: float):
+    """(kind, parameter) of hwbrj_rel_generate for the probe relation of a workload"""
+    return (2, -q) if q < 0 else (1, q)
 METRIC = "M input tuples/s ((|R|+|S|)/time)"
 UNIT = "Mtuples/s"
 
@@ -147,12 +155,12 @@ def cpu_reference_sample(wl, scale: int, nthreads: int, H, reps: int = 1):
     r2, s2, m2 = r // scale, s // scale, max(m // scale, 8) if variant is not None else 0
     if H.device_count() >= 1:  # the device generator makes the same key multiset in milliseconds
         dR = H.DeviceRelation.generate(0, r2, r2, 1.0, 1)
-        dS = H.DeviceRelation.generate(1, s2, r2, q, 2)
+        dS = H.DeviceRelation.generate(s_generator(q)[0], s2, r2, s_generator(q)[1], 2)
         R, S = dR.download(), dS.download()
         dR.free()
         dS.free()
     else:                      # no GPU here: the restated reference generator (generator.c) on the host
-        R, S = oracle.gen_R(r2), oracle.gen_S(s2, r2, q)
+        R, S = oracle.gen_R(r2), (oracle.gen_zipf(s2, r2, -q) if q < 0 else oracle.gen_S(s2, r2, q))
     use_ref = oracle.ref_available()
     times, res = [], None
     for _ in range(reps):
@@ -163,7 +171,7 @@ def cpu_reference_sample(wl, scale: int, nthreads: int, H, reps: int = 1):
             t0 = time.perf_counter()
             res = oracle.join(R, S, variant is not None, variant or 0, m2 or 8, k, B or 512)
             times.append(time.perf_counter() - t0)
-    sample = (f"1/{scale} of the workload: r={r2} s={s2} q={q} "
+    sample = (f"1/{scale} of the workload: r={r2} s={s2} " + (f"q={q} " if q >= 0 else f"zipf={-q} ")
               + (f"{'basic' if variant == 0 else 'blocked'} m={m2} k={k} B={B}" if variant is not None else "no filter")
               + ("; reference BPRO/PRO TOTAL-TIME-USECS" if use_ref else "; oracle port wall clock"))
     return {"times": times, "tuples": r2 + s2, "kind": "reference" if use_ref else "port",
@@ -232,7 +240,7 @@ def main():
 
     # ---- inputs (reference generator's multiset, generated on the device; synthetic) ----
     dR = H.DeviceRelation.generate(0, r, r, 1.0, 1)
-    dS = H.DeviceRelation.generate(1, s, r, q, 2)
+    dS = H.DeviceRelation.generate(s_generator(q)[0], s, r, s_generator(q)[1], 2)
 
     # ---- device-resident leg: `value` ----
     sampler = ClockSampler(local)
@@ -332,7 +340,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q,
+            "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q if q >= 0 else None, "zipf": -q if q < 0 else None,
                        "bloom": None if bloom is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
                        "radix_bits": stats[-1]["radix_bits"], "range_passes": stats[-1]["range_passes"],
                        "l2": f"inputs are {((r + s) * 8) >> 20} MiB per step, larger than the 126 MB L2; no flush needed",

@@ -189,7 +189,8 @@ class DeviceRelation:
 
     @classmethod
     def generate(cls, kind: int, n: int, r: int, q: float = 1.0, seed: int = 1) -> "DeviceRelation":
-        """kind 0: R (keys 1..n shuffled); kind 1: S (FK over r with selectivity q) -- generator.c closed form."""
+        """kind 0: R (keys 1..n shuffled); kind 1: S (FK over r with selectivity q) -- generator.c closed form;
+        kind 2: S = n Zipf foreign keys over 1..r with exponent q (create_relation_zipf, generator.c:659-676)."""
         return cls(N.load().hwbrj_rel_generate(kind, n, r, q, seed))
 
     def __len__(self) -> int:

@@ -44,7 +44,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     rlo, rcnt = chunk(r)
     slo, scnt = chunk(s)
     Rsh = ops.generate_shard(0, r, r, 1.0, 1, rlo, rcnt)
-    Ssh = ops.generate_shard(1, s, r, q, 2, slo, scnt)
+    Ssh = ops.generate_shard(2 if q < 0 else 1, s, r, -q if q < 0 else q, 2, slo, scnt)  # q < 0: Zipf exponent -q
 
     # exchanges fused into the partitioning kernels (NVLink peer stores); NCCL all-to-all is the fallback
     use_peer = os.environ.get("HWBRJ_DIST_PATH", "peer") == "peer"
@@ -149,7 +149,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q,
+                "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q if q >= 0 else None, "zipf": -q if q < 0 else None,
                            "bloom": None if bloom is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
                            "sharding": "contiguous chunks per rank; owner = filter-slice rank" if res["sliced_filter"] else "contiguous chunks per rank; owner = crapwow top bits",
                            "exchange": res.get("path", "nccl-all-to-all"),

@@ -106,6 +106,9 @@ struct Ctx {
     bool probe_staged = false;  // experimental: k >= 2 probes run on compacted candidates (k_probe_staged)
     bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
     DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
+    DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
+    uint64_t zipf_r = 0;
+    double zipf_theta = -1.0;
     int occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
     std::mutex mu;
 };
@@ -791,7 +794,26 @@ hwbrj_rel_t* hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double q
     rel->n_dev = nullptr;
     rel->n_expect = count;
     CK(cudaMalloc(&rel->d, std::max<uint64_t>(count, 2) * 8 + 64));
-    if (count) {
+    if (count && kind == 2) {
+        // Zipf foreign keys over the alphabet 1..r with exponent q (create_relation_zipf, generator.c:659-676)
+        const uint64_t alpha = std::min<uint64_t>(r ? r : 1, 0xFFFFFFFFull);
+        const uint32_t nchunks = (uint32_t)((alpha + kZipfChunk - 1) / kZipfChunk);
+        if (g.zipf_r != alpha || g.zipf_theta != q) {  // the cumulated-density table is kept for the next shard / call
+            g.zipf_lut.ensure(alpha * sizeof(double));
+            g.zipf_sums.ensure(((size_t)nchunks + 1) * sizeof(double));
+            k_zipf_scan_chunks<<<nchunks, 256, 0, g.stream>>>(g.zipf_lut.as<double>(), alpha, q, g.zipf_sums.as<double>());
+            k_zipf_scan_sums<<<1, 1024, 0, g.stream>>>(g.zipf_sums.as<double>(), nchunks);
+            k_zipf_finish<<<nchunks, 256, 0, g.stream>>>(g.zipf_lut.as<double>(), alpha, g.zipf_sums.as<double>(), nchunks);
+            g.zipf_r = alpha;
+            g.zipf_theta = q;
+        }
+        int bitsr = 1;
+        while ((1ull << bitsr) < alpha) bitsr++;
+        k_generate_zipf<<<g.sms * 8, 256, 0, g.stream>>>(rel->d, begin, count, g.zipf_lut.as<double>(), (uint32_t)alpha,
+                                                         (uint32_t)((bitsr + 1) / 2), seed * 0x9e3779b97f4a7c15ULL + 12345);
+        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaGetLastError());
+    } else if (count) {
         // generator.c:344: ntuples_above = num_tuples * (1 - selectivity)
         uint64_t na = kind == 1 ? (uint64_t)((double)n * (1.0 - q)) : 0;
         uint64_t nb = n - na;

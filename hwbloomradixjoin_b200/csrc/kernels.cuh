@@ -1218,4 +1218,105 @@ __global__ void k_generate(uint2* __restrict__ out, uint64_t n, int kind, uint64
     }
 }
 
+// ---- kind 2: Zipf-distributed foreign keys (create_relation_zipf, generator.c:659-676 -> genzipf.c) ------------------
+// Same construction as the reference: an alphabet = random permutation of 1..r (genzipf.c:27-52; here the Feistel
+// permutation), a lookup table of the cumulated density sum_{j<=i} j^-theta / sum_j j^-theta (:59-92), and per tuple a
+// uniform number with RAND_MAX resolution and the same binary search (:121-145). The reference draws from glibc rand()
+// serially; here tuple i draws from a counter-based generator of (i, seed), so a shard can be generated on its own.
+// Payload = position (the reference leaves it uninitialised, genzipf.c:147-148).
+constexpr int kZipfChunk = 4096;  // table entries per CTA of the blocked scan (256 threads x 16)
+
+// phase 1: terms j^-theta of one chunk, inclusive scan inside the chunk, chunk total to sums[chunk]
+__global__ void __launch_bounds__(256) k_zipf_scan_chunks(double* __restrict__ lut, uint64_t r, double theta,
+                                                         double* __restrict__ sums) {
+    __shared__ double warp_tot[8];
+    const uint64_t base = (uint64_t)blockIdx.x * kZipfChunk + (uint64_t)threadIdx.x * 16u;
+    double v[16], run = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint64_t j = base + i;  // table index, value index j+1
+        run += j < r ? 1.0 / pow((double)(j + 1), theta) : 0.0;
+        v[i] = run;
+    }
+    // exclusive scan of the per-thread totals over the CTA
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    double inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += u;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    double off = inc - run;
+    for (uint32_t w = 0; w < wid; w++) off += warp_tot[w];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if (base + i < r) lut[base + i] = off + v[i];
+    if (threadIdx.x == 255) sums[blockIdx.x] = off + run;
+}
+// phase 2 (one CTA): exclusive scan of the chunk totals in place, grand total to sums[nchunks]
+__global__ void __launch_bounds__(1024) k_zipf_scan_sums(double* __restrict__ sums, uint32_t nchunks) {
+    __shared__ double part[1024];
+    const uint32_t per = (nchunks + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per;
+    double local = 0.0;
+    for (uint32_t i = 0; i < per; i++)
+        if (lo + i < nchunks) local += sums[lo + i];
+    part[threadIdx.x] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // 1024 additions: not worth a parallel scan
+        double run = 0.0;
+        for (uint32_t t = 0; t < 1024u; t++) {
+            const double x = part[t];
+            part[t] = run;
+            run += x;
+        }
+        sums[nchunks] = run;
+    }
+    __syncthreads();
+    double run = part[threadIdx.x];
+    for (uint32_t i = 0; i < per; i++)
+        if (lo + i < nchunks) {
+            const double x = sums[lo + i];
+            sums[lo + i] = run;
+            run += x;
+        }
+}
+// phase 3: add the chunk offsets and normalise (lut[i] = sum / scaling_factor, genzipf.c:86-89)
+__global__ void __launch_bounds__(256) k_zipf_finish(double* __restrict__ lut, uint64_t r, const double* __restrict__ sums,
+                                                    uint32_t nchunks) {
+    const double total = sums[nchunks];
+    const double off = sums[blockIdx.x];
+    const uint64_t base = (uint64_t)blockIdx.x * kZipfChunk;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kZipfChunk; i += 256u)
+        if (base + i < r) lut[base + i] = (lut[base + i] + off) / total;
+}
+
+__global__ void k_generate_zipf(uint2* __restrict__ out, uint64_t begin, uint64_t count, const double* __restrict__ lut,
+                                uint32_t r, uint32_t half_bits_r, uint64_t seed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; li < count; li += stride) {
+        const uint64_t i = begin + li;
+        // uniform in [0,1] with the resolution of rand()/RAND_MAX (genzipf.c:124)
+        uint64_t z = i * 0x9e3779b97f4a7c15ULL + seed;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        z ^= z >> 31;
+        const double u = (double)(uint32_t)(z >> 33) / 2147483647.0;
+        uint32_t left = 0u, right = r - 1u, pos;
+        if (lut[0] >= u) pos = 0u;
+        else {
+            while (right - left > 1u) {
+                const uint32_t mid = (left + right) / 2u;
+                if (lut[mid] < u) left = mid;
+                else right = mid;
+            }
+            pos = right;
+        }
+        const uint32_t key = (uint32_t)feistel_perm(pos, r, half_bits_r, seed ^ 0x5bf03635ULL) + 1u;  // alphabet[pos]
+        out[li] = make_uint2(key, (uint32_t)i);
+    }
+}
+
 }  // namespace hwbrj

@@ -161,7 +161,10 @@ typedef struct hwbrj_rel hwbrj_rel_t; /* opaque device relation */
 hwbrj_rel_t * hwbrj_rel_upload(const tuple_t * tuples, uint64_t n);
 /* on-device generator with the reference generator's key multiset (generator.c:162-195,341-387):
  * kind 0: R = keys 1..n (payload = position); kind 1: S = FK relation over threshold r with selectivity q.
- * Positions are permuted by a seeded bijection (the reference's own shuffle is time-seeded). */
+ * Positions are permuted by a seeded bijection (the reference's own shuffle is time-seeded).
+ * kind 2: S = n Zipf-distributed foreign keys over the alphabet 1..r with exponent q (create_relation_zipf,
+ * generator.c:659-676 / genzipf.c: permuted alphabet, cumulated-density table, binary search per tuple; the uniform
+ * numbers come from a counter-based generator instead of glibc rand(), so the key ARRAY differs from a reference run). */
 hwbrj_rel_t * hwbrj_rel_generate(int kind, uint64_t n, uint64_t r, double q, uint64_t seed);
 int      hwbrj_rel_download(const hwbrj_rel_t * rel, tuple_t * out);
 uint64_t hwbrj_rel_size(const hwbrj_rel_t * rel);

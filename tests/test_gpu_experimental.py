@@ -65,3 +65,42 @@ def test_tuning_variant_matches_oracle(lib):
     if "no_" in lib or "only" in lib:
         pytest.skip("ablation build: results are wrong by construction")
     assert _run({"HWBRJ_LIB": os.path.join(ROOT, "build", "variants", lib)}) == []
+
+
+ZIPF_SCRIPT = r"""
+import json, math, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import hwbloomradixjoin_b200 as H
+H.set_quiet(True)
+n, r, theta = 3000001, 250000, 1.0
+bad = []
+dS = H.DeviceRelation.generate(2, n, r, theta, 7)
+S = dS.download()
+if not ((S["key"] >= 1).all() and (S["key"] <= r).all()): bad.append("keys outside the alphabet")
+if not (S["payload"] == np.arange(n, dtype=np.int64).astype(np.int32)).all(): bad.append("payload != position")
+cnt = np.sort(np.bincount(S["key"], minlength=r + 1))[::-1].astype(np.float64)
+Hn = sum(1.0 / (j ** theta) for j in range(1, r + 1))
+for rank in range(1, 6):  # the five most frequent keys follow n / (rank^theta * H)
+    exp = n / (rank ** theta * Hn)
+    if abs(cnt[rank - 1] - exp) > 6 * math.sqrt(exp): bad.append(["rank", rank, cnt[rank - 1], exp])
+# a shard generated on its own equals the slice of the whole relation
+from hwbloomradixjoin_b200 import _native as N
+import ctypes as C
+h = N.load().hwbrj_rel_generate_shard(2, n, r, theta, 7, 1000003, 500000)
+part = H.DeviceRelation(h).download()
+if not (part == S[1000003:1500003]).all(): bad.append("shard differs from the slice")
+# every Zipf key has a partner in R = 1..r: the join matches and the filter passes every S tuple
+dR = H.DeviceRelation.generate(0, r, r, 1.0, 1)
+res = H.join_device(dR, dS, H.BloomFilterArgs(0, 1 << 22, 1, 512))
+if (res.totalresults, res.filtered) != (n, n): bad.append(["join", res.totalresults, res.filtered])
+if res.checksum_key != int(S["key"].astype(np.uint64).sum()) %% (1 << 64): bad.append("key checksum")
+print(json.dumps(bad))
+"""
+
+
+def test_device_zipf_generator():
+    """kind 2 of hwbrj_rel_generate: alphabet, cumulated-density table and binary search of genzipf.c on the device"""
+    p = subprocess.run([sys.executable, "-c", ZIPF_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1]) == []

@@ -10,7 +10,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 r, s, q, variant, m, k, B, desc = WORKLOADS[name]
 H.set_quiet(True)
 dR = H.DeviceRelation.generate(0, r, r, 1.0, 1)
-dS = H.DeviceRelation.generate(1, s, r, q, 2)
+dS = H.DeviceRelation.generate(2 if q < 0 else 1, s, r, -q if q < 0 else q, 2)  # q < 0: Zipf exponent -q
 bloom = H.BloomFilterArgs(variant, m, k, B) if variant is not None else None
 for i in range(reps):
     res = H.join_device(dR, dS, bloom)

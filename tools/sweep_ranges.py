@@ -9,7 +9,7 @@ passes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2, 
 r, s, q, variant, m, k, B, desc = WORKLOADS[name]
 H.set_quiet(True)
 dR = H.DeviceRelation.generate(0, r, r, 1.0, 1)
-dS = H.DeviceRelation.generate(1, s, r, q, 2)
+dS = H.DeviceRelation.generate(2 if q < 0 else 1, s, r, -q if q < 0 else q, 2)  # q < 0: Zipf exponent -q
 bloom = H.BloomFilterArgs(variant, m, k, B)
 ref = None
 for nr in passes:
