@@ -51,7 +51,10 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     fabric = None
     if use_peer:
         try:  # the constructor fails on ALL ranks together when peer memory cannot be mapped -> NCCL all-to-all path
-            fabric = PeerFabric(ops, int(r / world * 1.2) + 65536, int(s / world * 1.2) + 65536)
+            # receive capacity per rank: 20 % over the even share; a Zipf probe relation sends its hot keys (all of
+            # them survive the filter) to single owners, so leave 2.5x there (overflow falls back to NCCL anyway)
+            s_slack = 2.5 if q < 0 else 1.2
+            fabric = PeerFabric(ops, int(r / world * 1.2) + 65536, int(s / world * s_slack) + 65536)
         except Exception as exc:
             print(f"[bench] NVLink peer path unavailable ({exc}); using NCCL all-to-all", flush=True)
 
