@@ -312,7 +312,7 @@ struct WarpRing {
     // ---- claim-ahead drains (HWBRJ_PROBE_CLAIM_AHEAD, untested on hardware yet): the output space of a drain is
     // claimed at the end of one iteration and written at the start of the next, after that iteration's loads have
     // been issued, so the round trip of the atomic on the shared cursor is hidden. Capacity: fewer than CAP/2 tuples
-    // are left after complete(), one iteration appends at most CAP/2.
+    // are left after complete(); if one iteration can append more than CAP/2, make_room() drains in place.
     unsigned long long priv_next;  // HWBRJ_K2_ABLATE & 2 only
     unsigned long long pend_base;  // valid in lane 0 while pending
     bool pending;                  // warp-uniform
@@ -332,6 +332,14 @@ struct WarpRing {
         count -= CAP / 2;
         pending = false;
         __syncwarp();
+    }
+    // claim-ahead safety valve: rings smaller than one iteration's worst case (64 x kProbeV tuples) drain in place
+    // before the next append2 (which adds up to 64) could overflow them
+    __device__ __forceinline__ void make_room(uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol, uint32_t lane) {
+        if (count > (uint32_t)(CAP - 64)) {
+            complete(out, pol, lane);
+            if (count > (uint32_t)(CAP - 64)) drain(CAP / 2, out, cursor, pol, lane);
+        }
     }
     // at most 64 tuples are appended between two calls, so one drain of CAP/2 keeps the ring from overflowing
     __device__ __forceinline__ void drain_if_full(uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol, uint32_t lane) {
@@ -445,6 +453,7 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
             surv.append2(fa, ta, fb, tb, lt);
 #if HWBRJ_PROBE_CLAIM_AHEAD
             if (kDefer) surv.drain_if_full(out, out_cursor, pol, lane);
+            else if (64 * kProbeV > kSurvCap / 2) surv.make_room(out, out_cursor, pol, lane);  // compile-time condition
 #else
             surv.drain_if_full(out, out_cursor, pol, lane);
 #endif

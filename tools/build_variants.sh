@@ -16,6 +16,9 @@ d_claim_ring128_m4|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128 -DHWBRJ_PR
 e_claim_ring128_m5_c5|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128 -DHWBRJ_PROBE_MINBLOCKS=5
 f_ld_cg_all|-DHWBRJ_PROBE_LD=2
 g_ld_ldg_all|-DHWBRJ_PROBE_LD=0
+h_v8_m2_c2|-DHWBRJ_PROBE_V=8 -DHWBRJ_PROBE_MINBLOCKS=2
+i_v8_m3_c3|-DHWBRJ_PROBE_V=8 -DHWBRJ_PROBE_MINBLOCKS=3
+j_v2_m6_c6_claim_ring128|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=6 -DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128
 ' ;;
 ablate) list='
 a_base|
