@@ -259,6 +259,25 @@ def test_heavily_skewed_partitions(Hgpu, oracle_mod):
         assert (res.totalresults, res.checksum_pair, res.checksum_key) == (exp["matches"], exp["checksum_pair"], exp["checksum_key"])
 
 
+def test_one_key_dominates_the_probe_relation(Hgpu, oracle_mod):
+    """more than 4 M probe tuples in ONE partition: its > 128 work items are written by the whole CTA of k_worklist and
+    processed by many CTAs of k_join (what a Zipf-skewed S does at full size)"""
+    R = np.zeros(60_000, dtype=Hgpu.TUPLE)
+    R["key"] = np.arange(1, R.shape[0] + 1)
+    R["key"][:3] = 77  # the hot key has three build tuples: three pairs per hot probe tuple
+    R["payload"] = np.arange(R.shape[0]) + 11
+    S = np.zeros(5_300_000, dtype=Hgpu.TUPLE)
+    S["key"] = 77
+    S["key"][::9] = (np.arange(0, S.shape[0], 9) % 120_000) + 1
+    S["payload"] = np.arange(S.shape[0])
+    for args, oargs in [(None, (False,)), (Hgpu.BloomFilterArgs(0, 1 << 21, 1, 512), (True, 0, 1 << 21, 1, 512))]:
+        res = Hgpu.run("PRO", R, S, 1, args)
+        exp = oracle_mod.join(R, S, *oargs)
+        assert (res.totalresults, res.checksum_pair, res.checksum_key) == (exp["matches"], exp["checksum_pair"], exp["checksum_key"])
+        if args is not None:
+            assert res.filtered == exp["filtered"]
+
+
 def test_zipf_probe_relation(Hgpu, oracle_mod):
     """BASELINE config 5 (-z 1.0) at a CPU-checkable size: every S tuple matches and passes the filter"""
     r, s = 200_000, 1_500_000
