@@ -21,7 +21,16 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, cases, out_q):
+def _inputs(oracle, zipf):
+    R = oracle.gen_R(60_000, nthreads=2)
+    if zipf:  # BASELINE config 5: hot foreign keys, every probe tuple has a partner and passes the filter
+        S = oracle.gen_zipf(300_001, 60_000, 1.0)
+    else:
+        S = oracle.gen_S(400_001, 60_000, 0.05, nthreads=2)
+    return R, S
+
+
+def _worker(rank, world, port, cases, out_q, zipf=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -32,8 +41,7 @@ def _worker(rank, world, port, cases, out_q):
     from hwbloomradixjoin_b200 import BloomFilterArgs
     from hwbloomradixjoin_b200.dist import dist_join
     ops = OracleOps()
-    R = oracle.gen_R(60_000, nthreads=2)
-    S = oracle.gen_S(400_001, 60_000, 0.05, nthreads=2)
+    R, S = _inputs(oracle, zipf)
     # contiguous chunks like the reference's per-thread split (last rank takes the remainder, :1646-1670)
     def chunk(a):
         per = a.shape[0] // world
@@ -83,6 +91,29 @@ def test_sharded_join_matches_single_process_oracle(world, oracle_mod):
         assert got["sliced_filter"] == expect_sliced
         if case is not None:  # the filter cuts the exchanged volume: only survivors cross the wire
             assert got["tuples_over_nvlink_s"] <= exp["filtered"]
+
+
+def test_sharded_join_with_zipf_skew(oracle_mod):
+    """owners receive very different numbers of probe tuples (the hottest key alone is ~9 % of S): the exchange must
+    cope with ragged counts, and since every Zipf key exists in R all of S matches and survives the filter"""
+    world, cases = 4, [(0, 1 << 19, 1, 512), (1, 1 << 19, 4, 256), None]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    R, S = _inputs(oracle_mod, True)
+    for case, got in zip(cases, results):
+        exp = oracle_mod.join(R, S, case is not None, *(case or ()))
+        assert got["matches"] == exp["matches"] == S.shape[0]
+        assert got["filtered"] == (S.shape[0] if case is not None else -1)
+        for f in ("checksum_pair", "checksum_rpay", "checksum_spay", "checksum_key"):
+            assert got[f] == exp[f], (case, f)
 
 
 def test_scalar_reduction_is_exact_mod_2_64():
