@@ -104,3 +104,36 @@ def test_device_zipf_generator():
     p = subprocess.run([sys.executable, "-c", ZIPF_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert json.loads(p.stdout.strip().splitlines()[-1]) == []
+
+
+RANDOM_SCRIPT = r"""
+import json, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import oracle
+import hwbloomradixjoin_b200 as H
+H.set_quiet(True)
+rng = np.random.default_rng(77)
+R = np.zeros(40_000, dtype=H.TUPLE); R["key"] = rng.integers(-2**31, 2**31, R.shape[0], dtype=np.int64).astype(np.int32)
+R["payload"] = np.arange(R.shape[0])
+S = np.zeros(300_000, dtype=H.TUPLE); S["key"] = rng.integers(-2**31, 2**31, S.shape[0], dtype=np.int64).astype(np.int32)
+S["key"][:20000] = R["key"][rng.integers(0, R.shape[0], 20000)]; S["payload"] = np.arange(S.shape[0])
+bad = []
+for i in range(64):
+    variant = int(rng.integers(0, 2)); log2m = int(rng.integers(10, 23)); k = int(rng.integers(0, 13))
+    B = 1 << int(rng.integers(3, log2m + 1)); m = 1 << log2m
+    args = H.BloomFilterArgs(variant, m, k, B)
+    if not (H.bloom_build(R, args) == oracle.bloom_build(R, variant, m, k, B)).all(): bad.append(["bitmap", variant, m, k, B])
+    r = H.BPRO(R, S, 2, args); o = oracle.join(R, S, True, variant, m, k, B)
+    if (r.totalresults, r.filtered, r.checksum_pair) != (o["matches"], o["filtered"], o["checksum_pair"]):
+        bad.append(["join", variant, m, k, B])
+print(json.dumps(bad))
+"""
+
+
+def test_random_filter_points_match_oracle():
+    """64 seeded random (variant, m = 2^10..2^22, k = 0..12, B = 8..m) points on full-range int32 keys; to be promoted
+    into test_gpu_parity.py once it has run on hardware"""
+    p = subprocess.run([sys.executable, "-c", RANDOM_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1]) == []

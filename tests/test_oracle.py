@@ -167,6 +167,54 @@ def test_oracle_filter_vs_compiled_reference(oracle_mod):
         assert oracle_mod.bloom_filter(a, S, variant, m, k, B) == oracle_mod.ref_bloom_count(b, S, variant, m, k, B)
 
 
+def _random_filter_configs(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        variant = int(rng.integers(0, 2))
+        log2m = int(rng.integers(10, 23))
+        k = int(rng.integers(0, 13))
+        log2B = int(rng.integers(3, log2m + 1))  # B = 8 ... m
+        out.append((variant, 1 << log2m, k, 1 << log2B))
+    return out
+
+
+def test_random_filter_configs_vs_compiled_reference(oracle_mod):
+    """48 seeded random (variant, m, k, B) points: bitmap byte-equality and the probe count against the unmodified
+    reference, on keys that cover the whole int32 range"""
+    _need_ref(oracle_mod)
+    rng = np.random.default_rng(2024)
+    R = np.zeros(20_000, dtype=oracle_mod.TUPLE)
+    R["key"] = rng.integers(-2**31, 2**31, R.shape[0], dtype=np.int64).astype(np.int32)
+    S = np.zeros(60_000, dtype=oracle_mod.TUPLE)
+    S["key"] = rng.integers(-2**31, 2**31, S.shape[0], dtype=np.int64).astype(np.int32)
+    S["key"][:5000] = R["key"][:5000]
+    for variant, m, k, B in _random_filter_configs(48, 11):
+        a = oracle_mod.bloom_build(R, variant, m, k, B)
+        b = oracle_mod.ref_bloom_build(R, variant, m, k, B)
+        assert (a == b).all(), (variant, m, k, B)
+        assert oracle_mod.bloom_filter(a, S, variant, m, k, B) == oracle_mod.ref_bloom_count(b, S, variant, m, k, B), \
+            (variant, m, k, B)
+
+
+@pytest.mark.parametrize("cfg", _random_filter_configs(8, 5), ids=lambda c: f"v{c[0]}-m{c[1]}-k{c[2]}-B{c[3]}")
+def test_random_join_configs_vs_compiled_reference(oracle_mod, cfg):
+    """the whole join (matches, filtered, pair checksums) at seeded random filter settings, duplicate build keys included"""
+    _need_ref(oracle_mod, mat=True)
+    variant, m, k, B = cfg
+    rng = np.random.default_rng(m + k)
+    R = np.zeros(40_000, dtype=oracle_mod.TUPLE)
+    R["key"] = rng.integers(1, 30_000, R.shape[0]).astype(np.int32)  # duplicates: several pairs per probe tuple
+    R["payload"] = np.arange(R.shape[0])
+    S = np.zeros(250_000, dtype=oracle_mod.TUPLE)
+    S["key"] = rng.integers(1, 300_000, S.shape[0]).astype(np.int32)
+    S["payload"] = np.arange(S.shape[0]) + 1_000_000
+    ref = oracle_mod.ref_join(R, S, "PRO", 4, True, variant, m, k, B, mat=True)
+    orc = oracle_mod.join(R, S, True, variant, m, k, B)
+    for f in ("matches", "filtered", "checksum_pair", "checksum_rpay", "checksum_spay"):
+        assert ref[f] == orc[f], (cfg, f)
+
+
 def test_zipf_generator_vs_reference(oracle_mod):
     _need_ref(oracle_mod)
     a = oracle_mod.gen_zipf(200_000, 50_000, 1.0, seed=54321)
