@@ -104,6 +104,8 @@ struct Ctx {
     int probe_ctas_per_sm = 0;  // 0 = occupancy API
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
     bool probe_staged = false;  // experimental: k >= 2 probes run on compacted candidates (k_probe_staged)
+    bool route_precount = false;  // experimental: hwbrj_route_peer claims once per owner (k_route_claim)
+    DevBuf route_hist, route_cur;
     bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
     DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
     DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
@@ -152,6 +154,7 @@ static void init_ctx() {
     if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_CARVEOUT")) g.probe_carveout = std::min(100, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_STAGED")) g.probe_staged = atoi(s) != 0;
+    if (const char* s = getenv("HWBRJ_ROUTE_PRECOUNT")) g.route_precount = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_DEFER")) g.defer_ranges = atoi(s) != 0;
     CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
     CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
@@ -1228,6 +1231,20 @@ int hwbrj_route_peer(const hwbrj_rel_t* in, int world, const bloom_filter_args_t
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_scatter<4, true>, kScatterThreads, kScatterSmem));
         occ3 = std::max(occ3, 1);
         occ4 = std::max(occ4, 1);
+    }
+    if (g.route_precount) {  // experimental: one remote claim per owner instead of one per (tile, owner)
+        g.route_hist.ensure(kMaxPeers * sizeof(uint32_t));
+        g.route_cur.ensure(kMaxPeers * sizeof(unsigned long long));
+        CK(cudaMemsetAsync(g.route_hist.p, 0, kMaxPeers * sizeof(uint32_t), g.stream));
+        if (mode == 4)
+            k_owner_hist<4><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, in->n_dev, fn, g.d_crc, (uint32_t)world,
+                                                             g.route_hist.as<uint32_t>());
+        else
+            k_owner_hist<3><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, in->n_dev, fn, g.d_crc, (uint32_t)world,
+                                                             g.route_hist.as<uint32_t>());
+        k_route_claim<<<1, 32, 0, g.stream>>>(g.route_hist.as<uint32_t>(), pt, (uint32_t)world,
+                                              g.route_cur.as<unsigned long long>());
+        for (int i = 0; i < world; i++) pt.cursor[i] = g.route_cur.as<unsigned long long>() + i;  // local sub-allocation
     }
     if (mode == 4)
         k_scatter<4, true><<<g.sms * occ4, kScatterThreads, kScatterSmem, g.stream>>>(

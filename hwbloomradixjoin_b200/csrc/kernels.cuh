@@ -780,6 +780,23 @@ struct PeerTargets {
     unsigned int* overflow;                 // local flag, set when a claim does not fit
 };
 
+// Pre-counted routing (experimental, HWBRJ_ROUTE_PRECOUNT=1): instead of one system-scope atomic per (tile, owner) on the
+// owners' cursors -- 8 GPUs x 7 800 tiles hammer the same 8 addresses over NVLink -- the sender counts its tuples per
+// owner first (k_owner_hist), claims its whole range on every owner with ONE remote atomic each, and the scatter kernel
+// sub-allocates from local cursors that start at the claimed bases.
+__global__ void k_route_claim(const uint32_t* __restrict__ counts, PeerTargets peers, uint32_t world,
+                              unsigned long long* __restrict__ local_cursor) {
+    const uint32_t b = threadIdx.x;
+    if (b >= world) return;
+    const unsigned long long tot = counts[b];
+    unsigned long long base = tot ? atomicAdd_system(peers.cursor[b], tot) : 0ull;
+    if (base + tot > peers.capacity) {  // does not fit: every later sub-claim lands beyond the capacity and is dropped
+        atomicExch(peers.overflow, 1u);
+        base = peers.capacity;
+    }
+    local_cursor[b] = base;
+}
+
 template <int MODE, bool REMOTE = false>
 __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
                                                             const uint64_t* __restrict__ n_ptr, uint64_t n_static,

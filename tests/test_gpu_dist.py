@@ -54,11 +54,21 @@ dist.destroy_process_group()
 
 
 def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path):
+    _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, {})
+
+
+@pytest.mark.skipif(os.environ.get("HWBRJ_TEST_EXPERIMENTAL") != "1", reason="experimental: set HWBRJ_TEST_EXPERIMENTAL=1")
+def test_two_gpu_join_with_precounted_routing(Hgpu, tmp_path):
+    """HWBRJ_ROUTE_PRECOUNT=1: one remote claim per owner (k_route_claim) instead of one per (tile, owner)"""
+    _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, {"HWBRJ_ROUTE_PRECOUNT": "1"})
+
+
+def _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, extra_env):
     if Hgpu.device_count() < 2:
         pytest.skip("needs 2 GPUs (one rank per GPU)")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, HWBRJ_ROOT=ROOT)
+    env = dict(os.environ, HWBRJ_ROOT=ROOT, **extra_env)
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                        capture_output=True, text=True, env=env, timeout=600)
