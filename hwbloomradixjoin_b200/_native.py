@@ -48,7 +48,7 @@ class StatsT(C.Structure):  # hwbrj_stats_t
 EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_last_stats", "hwbrj_last_filtered",
            "hwbrj_last_checksum", "hwbrj_last_filter", "hwbrj_set_quiet", "hwbrj_set_radix_bits", "hwbrj_set_range_passes", "hwbrj_set_overlap_h2d", "hwbrj_set_hash_partition", "hwbrj_version",
            "hwbrj_device_count", "hwbrj_check_args", "hwbrj_rel_upload", "hwbrj_rel_generate", "hwbrj_rel_download",
-           "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_join_device_async", "hwbrj_host_alloc", "hwbrj_host_free",
+           "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_join_device_async", "hwbrj_join_prepare_r", "hwbrj_host_alloc", "hwbrj_host_free",
            "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_fpr_count", "hwbrj_materialize_last", "hwbrj_materialize_last_device", "hwbrj_radix_partition",
            "hwbrj_set_stream", "hwbrj_reset_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
            "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe",
@@ -99,6 +99,8 @@ def load():
     L.hwbrj_rel_free.argtypes = [C.c_void_p]
     L.hwbrj_join_device.argtypes = [C.c_void_p, C.c_void_p, argp, C.POINTER(StatsT)]
     L.hwbrj_join_device_async.argtypes = [C.c_void_p, C.c_void_p, argp, C.c_void_p]
+    L.hwbrj_join_prepare_r.restype = C.c_int
+    L.hwbrj_join_prepare_r.argtypes = [C.c_void_p]
     L.hwbrj_host_alloc.restype = C.c_void_p
     L.hwbrj_host_alloc.argtypes = [C.c_uint64]
     L.hwbrj_host_free.argtypes = [C.c_void_p]

@@ -104,8 +104,20 @@ struct Ctx {
     int probe_ctas_per_sm = 0;  // 0 = occupancy API
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
     bool probe_staged = false;  // experimental: k >= 2 probes run on compacted candidates (k_probe_staged)
+    // R side of a filter-less join partitioned ahead of time on the side stream (hwbrj_join_prepare_r)
+    struct {
+        bool valid = false;
+        const uint2* d = nullptr;
+        uint64_t n = 0;
+        const unsigned long long* n_dev = nullptr;
+        int bits = 0;
+        const uint2* Rp = nullptr;
+        int launches = 0;
+    } prep;
+    cudaEvent_t ev_prep_fork = nullptr, ev_prep_done = nullptr;
     bool route_precount = false;  // experimental: hwbrj_route_peer claims once per owner (k_route_claim)
     DevBuf route_hist, route_cur;
+    DevBuf histF;  // one-bin histogram of filter-only builds while histR belongs to a prepared R partitioning
     bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
     DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
     DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
@@ -136,6 +148,8 @@ static void init_ctx() {
     for (auto& ev : g.ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char* s = getenv("HWBRJ_OVERLAP_H2D")) g.overlap_h2d = atoi(s) != 0;
     for (auto& ev : g.ev_side) CK(cudaEventCreate(&ev));
+    CK(cudaEventCreateWithFlags(&g.ev_prep_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_prep_done, cudaEventDisableTiming));
     if (const char* s = getenv("HWBRJ_OVERLAP")) g.overlap_r_partition = atoi(s) != 0;
     CrcTables T;
     crc_tables_fill(T);
@@ -442,7 +456,10 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
     if (args && nS_dev) die("device-side S count is only supported for the filter-less join");
     ensure_workspace(nR, nS, args);
-    const int bits = pick_bits(nR_dev ? nR_expect : nR);
+    // the R side may have been partitioned already (hwbrj_join_prepare_r, filter-less joins of exactly this relation)
+    const bool prepared = !args && g.prep.valid && g.prep.d == dR && g.prep.n == nR && g.prep.n_dev == nR_dev;
+    g.prep.valid = false;  // one use; a stale preparation of another relation is simply dropped
+    const int bits = prepared ? g.prep.bits : pick_bits(nR_dev ? nR_expect : nR);
     const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
     const uint32_t P = 1u << bits;
     const uint32_t pmask = P - 1u;
@@ -452,7 +469,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     // ---- untimed set-up (the reference allocates and zeroes its filter before the timed region, :1583) ----
     rec(g.ev[0], g.stream);
     if (args) CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
-    CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
+    if (!prepared) CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));  // else: in use on the side stream
     CK(cudaMemsetAsync(g.histS.p, 0, P * 4, g.stream));
     CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
 
@@ -492,7 +509,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
                 launches++;
             }
         }
-    } else {
+    } else if (!prepared) {
         k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
         launches++;
     }
@@ -500,7 +517,10 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
     // R partitioning (HBM-bound) runs on a side stream underneath the S probe (L1TEX/issue-bound) when a filter is used
     const bool overlap = g.overlap_r_partition && args != nullptr;
     const uint2* Rp;
-    if (overlap) {
+    if (prepared) {
+        Rp = g.prep.Rp;  // partitioned on the side stream; joined below, before the work list
+        launches += g.prep.launches;
+    } else if (overlap) {
         CK(cudaStreamWaitEvent(g.side_stream, g.ev[2], 0));
         rec(g.ev_side[0], g.side_stream);
         Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(), g.rt1.as<uint2>(),
@@ -550,6 +570,7 @@ static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
                                     g.st1.as<uint2>(), g.sc.as<uint2>(), launches, nullptr, false, pf);
     rec(g.ev[5], g.stream);
     if (overlap) CK(cudaStreamWaitEvent(g.stream, g.ev_side[1], 0));
+    if (prepared) CK(cudaStreamWaitEvent(g.stream, g.ev_prep_done, 0));
     k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>(),
                                          g.work_part.as<uint32_t>());
     launches++;
@@ -906,6 +927,36 @@ int hwbrj_join_device_async(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bl
     run_join(R->d, R->n, S->d, S->n, args, st, R->n_dev, R->n_expect, S->n_dev, nullptr,
              reinterpret_cast<unsigned long long*>(d_out6));
     return st.kernel_launches;
+}
+
+int hwbrj_join_prepare_r(const hwbrj_rel_t* R) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    init_ctx();
+    if (!R || R->n >= (1ull << 32) - (1ull << 20)) return -1;
+    ensure_workspace(R->n, 1, nullptr);
+    const int bits = pick_bits(R->n_dev ? R->n_expect : R->n);
+    const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
+    const uint32_t P = 1u << bits;
+    BloomParams bp;
+    memset(&bp, 0, sizeof(bp));
+    // fork from the caller's stream: everything R depends on has been enqueued there
+    CK(cudaEventRecord(g.ev_prep_fork, g.stream));
+    CK(cudaStreamWaitEvent(g.side_stream, g.ev_prep_fork, 0));
+    CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.side_stream));
+    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + kCrcSmemWords) * 4), g.side_stream>>>(
+        R->d, R->n, R->n_dev, bp, g.d_crc, g.histR.as<uint32_t>(), P - 1u);
+    int launches = 1;
+    g.prep.Rp = run_partition(R->d, R->n, R->n_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(),
+                              g.rt1.as<uint2>(), g.rp.as<uint2>(), launches, g.side_stream, true);
+    CK(cudaEventRecord(g.ev_prep_done, g.side_stream));
+    CK(cudaGetLastError());
+    g.prep.valid = true;
+    g.prep.d = R->d;
+    g.prep.n = R->n;
+    g.prep.n_dev = R->n_dev;
+    g.prep.bits = bits;
+    g.prep.launches = launches;
+    return launches;
 }
 
 void* hwbrj_host_alloc(uint64_t bytes) {
@@ -1284,16 +1335,21 @@ int hwbrj_filter_build(const hwbrj_rel_t* R, const bloom_filter_args_t* args, vo
     init_ctx();
     if (!R || !args || !d_filter || check_args_impl(args, true)) return -1;
     g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
+    // the (unused) one-bin histogram of the insert kernel: histR, unless a prepared R partitioning owns histR right now
+    uint32_t* hist = g.histR.as<uint32_t>();
+    if (g.prep.valid) {
+        g.histF.ensure(256);
+        hist = g.histF.as<uint32_t>();
+    }
     if (zero_first) CK(cudaMemsetAsync(d_filter, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
-    CK(cudaMemsetAsync(g.histR.p, 0, 4, g.stream));
+    CK(cudaMemsetAsync(hist, 0, 4, g.stream));
     BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(d_filter));
     int nranges = pick_ranges(args);
     bp.nranges = (uint32_t)nranges;
     bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, R->n_dev, bp, g.d_crc,
-                                                                          g.histR.as<uint32_t>(), 0u);
+        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, R->n_dev, bp, g.d_crc, hist, 0u);
     }
     CK(cudaGetLastError());
     return 0;

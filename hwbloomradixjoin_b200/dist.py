@@ -21,6 +21,7 @@ backend (tests provide an oracle-backed ops object); the only production impleme
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -368,6 +369,8 @@ def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Ssh
     fabric.barrier()
     tm.mark("route_r_fused")
     Rown = L.hwbrj_rel_wrap_counted(fabric.local[0], fabric.cap_r, ctrl, max(r_total // world, 1))
+    if os.environ.get("HWBRJ_DIST_OVERLAP_R") == "1" and L.hwbrj_join_prepare_r(Rown) < 0:  # experimental, see below
+        raise RuntimeError("hwbrj_join_prepare_r failed")
     # (2) filter slice / partial + combine, (3) local pre-filter
     if bloom is not None:
         filt = torch.empty(max(bloom.m // 8, 16), dtype=torch.uint8, device=ops.device)
@@ -447,6 +450,11 @@ def _peer_pipeline_async(ops: "CudaOps", fabric: PeerFabric, Rshard, Sshard, blo
     Rown = L.hwbrj_rel_wrap_counted(fabric.local[0], fabric.cap_r, ctrl, max(r_total // world, 1))
     cnt = torch.zeros(1, dtype=torch.int64, device=ops.device)
     keep.append(cnt)
+    if os.environ.get("HWBRJ_DIST_OVERLAP_R") == "1":
+        # experimental: the owned R is partitioned on the library's side stream while this stream builds, gathers and
+        # probes the filter; the local join at the end picks the partitions up (hwbrj_join_prepare_r)
+        if L.hwbrj_join_prepare_r(Rown) < 0:
+            raise RuntimeError("hwbrj_join_prepare_r failed")
     if bloom is not None:
         filt = torch.empty(max(bloom.m // 8, 16), dtype=torch.uint8, device=ops.device)
         bc = bloom.to_c()

@@ -178,6 +178,12 @@ int hwbrj_join_device(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_
  * collectives around it). Leaves {matches, checksum_pair, checksum_rpay, checksum_spay, checksum_key, filtered}
  * as six uint64 in d_out6 (device). Returns the number of kernels enqueued, < 0 on error. */
 int hwbrj_join_device_async(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args, void * d_out6);
+/* Partition the build side of a FILTER-LESS join ahead of time: the histogram and scatter passes of R (the R half of
+ * :808-849) are enqueued on a library-owned side stream forked from the current stream, so that they overlap whatever the
+ * caller enqueues next (the multi-GPU join: filter all-gather and S probe). The next hwbrj_join_device[_async](R, S, NULL)
+ * on the same relation joins the side stream and skips those passes. Returns the number of kernel launches, < 0 on
+ * error. Experimental (HWBRJ_DIST_OVERLAP_R=1 in hwbloomradixjoin_b200.dist). */
+int hwbrj_join_prepare_r(const hwbrj_rel_t * R);
 
 /* pinned host buffers for callers that want full-speed PCIe copies (bench e2e leg) */
 void * hwbrj_host_alloc(uint64_t bytes);

@@ -63,6 +63,18 @@ def test_two_gpu_join_with_precounted_routing(Hgpu, tmp_path):
     _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, {"HWBRJ_ROUTE_PRECOUNT": "1"})
 
 
+@pytest.mark.skipif(os.environ.get("HWBRJ_TEST_EXPERIMENTAL") != "1", reason="experimental: set HWBRJ_TEST_EXPERIMENTAL=1")
+def test_two_gpu_join_with_r_partitioned_ahead(Hgpu, tmp_path):
+    """HWBRJ_DIST_OVERLAP_R=1: the owned R is partitioned on a side stream under the filter exchange and the S probe
+    (hwbrj_join_prepare_r), eager and captured in the CUDA graph"""
+    _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, {"HWBRJ_DIST_OVERLAP_R": "1"})
+
+
+@pytest.mark.skipif(os.environ.get("HWBRJ_TEST_EXPERIMENTAL") != "1", reason="experimental: set HWBRJ_TEST_EXPERIMENTAL=1")
+def test_two_gpu_join_with_both_experimental_paths(Hgpu, tmp_path):
+    _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, {"HWBRJ_DIST_OVERLAP_R": "1", "HWBRJ_ROUTE_PRECOUNT": "1"})
+
+
 def _two_gpu_join_equals_single_gpu(Hgpu, tmp_path, extra_env):
     if Hgpu.device_count() < 2:
         pytest.skip("needs 2 GPUs (one rank per GPU)")
