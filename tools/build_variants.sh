@@ -1,6 +1,8 @@
 #!/bin/bash
 # development helper: compile tuning variants of the library into build/variants/ (run here, they travel with gpurun);
-# then `bash tools/sweep_variants.sh <workload>` on the GPU box times each one. One "name|nvcc -D flags" per line.
+# then `bash tools/sweep_variants.sh <workload>` on the GPU box times each one. One "name|nvcc -D flags" per line; a
+# "_c<N>" / "_o<NN>" in the name makes the sweep set HWBRJ_PROBE_CTAS=N / HWBRJ_PROBE_CARVEOUT=NN for that run (k vs l:
+# same small-ring kernel with the large L1 it allows and with the L1 of the 512-tuple ring -> drain size vs L1 size).
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build/variants
@@ -19,6 +21,9 @@ g_ld_ldg_all|-DHWBRJ_PROBE_LD=0
 h_v8_m2_c2|-DHWBRJ_PROBE_V=8 -DHWBRJ_PROBE_MINBLOCKS=2
 i_v8_m3_c3|-DHWBRJ_PROBE_V=8 -DHWBRJ_PROBE_MINBLOCKS=3
 j_v2_m6_c6_claim_ring128|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=6 -DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128
+k_ring128_m4|-DHWBRJ_PROBE_RING=128 -DHWBRJ_PROBE_MINBLOCKS=4
+l_ring128_m4_o58|-DHWBRJ_PROBE_RING=128 -DHWBRJ_PROBE_MINBLOCKS=4
+m_claim_ring128_m4_o58|-DHWBRJ_PROBE_CLAIM_AHEAD=1 -DHWBRJ_PROBE_RING=128 -DHWBRJ_PROBE_MINBLOCKS=4
 ' ;;
 ablate) list='
 a_base|
