@@ -53,8 +53,11 @@ UNIT = "Mtuples/s"
 
 def ncu_traffic(kernel_key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json; null when there is no capture for this workload)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    `ncu --set full` capture (profiles/r2_traffic.json, else r1_traffic.json; null when there is no capture for this
+    workload)."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         return json.load(open(p)).get(kernel_key)
     except Exception:
@@ -148,57 +151,72 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_reference_sample(wl, scale: int, nthreads: int, H, reps: int = 1):
-    """The unmodified reference on the host cores, on a 1/scale copy of the workload (same |S|/|R|, q, m/|R|, k)."""
-    import oracle
+def wl_config(name, wl):
+    """the `config` object both arms print (identical: the driver compares them)"""
+    r, s, q, variant, m, k, B, desc = wl
+    return {"workload": desc, "name": name, "r": r, "s": s, "q": q if q >= 0 else None, "zipf": -q if q < 0 else None,
+            "bloom": None if variant is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
+            "l2": f"inputs are {((r + s) * 8) >> 20} MiB per step, larger than the 126 MB L2 (and the host LLC); no flush needed"}
+
+
+def scaled(wl, scale: int):
+    r, s, q, variant, m, k, B, desc = wl
+    if scale == 1:
+        return wl
+    return (r // scale, s // scale, q, variant, max(m // scale, 8) if variant is not None else 0, k, B, desc)
+
+
+def sample_text(wl, scale: int, use_ref: bool) -> str:
     r, s, q, variant, m, k, B, _ = wl
-    r2, s2, m2 = r // scale, s // scale, max(m // scale, 8) if variant is not None else 0
-    if H.device_count() >= 1:  # the device generator makes the same key multiset in milliseconds
-        dR = H.DeviceRelation.generate(0, r2, r2, 1.0, 1)
-        dS = H.DeviceRelation.generate(s_generator(q)[0], s2, r2, s_generator(q)[1], 2)
-        R, S = dR.download(), dS.download()
-        dR.free()
-        dS.free()
-    else:                      # no GPU here: the restated reference generator (generator.c) on the host
-        R, S = oracle.gen_R(r2), (oracle.gen_zipf(s2, r2, -q) if q < 0 else oracle.gen_S(s2, r2, q))
-    use_ref = oracle.ref_available()
-    times, res = [], None
-    for _ in range(reps):
-        if use_ref:
-            res = oracle.ref_join(R, S, "PRO", nthreads, variant is not None, variant or 0, m2 or 8, k, B or 512)
-            times.append(res["total_usecs"] * 1e-6)
-        else:
-            t0 = time.perf_counter()
-            res = oracle.join(R, S, variant is not None, variant or 0, m2 or 8, k, B or 512)
-            times.append(time.perf_counter() - t0)
-    sample = (f"1/{scale} of the workload: r={r2} s={s2} " + (f"q={q} " if q >= 0 else f"zipf={-q} ")
-              + (f"{'basic' if variant == 0 else 'blocked'} m={m2} k={k} B={B}" if variant is not None else "no filter")
-              + ("; reference BPRO/PRO TOTAL-TIME-USECS" if use_ref else "; oracle port wall clock"))
-    return {"times": times, "tuples": r2 + s2, "kind": "reference" if use_ref else "port",
-            "cores": nthreads if use_ref else 1, "sample": sample, "result": res}
+    head = "the full workload" if scale == 1 else f"1/{scale} of the workload (same |S|/|R|, q, m/|R|, k)"
+    return (f"{head}: r={r} s={s} " + (f"q={q} " if q >= 0 else f"zipf={-q} ")
+            + (f"{'basic' if variant == 0 else 'blocked'} m={m} k={k} B={B}" if variant is not None else "no filter")
+            + ("; unmodified reference BPRO/PRO, its own TOTAL-TIME-USECS" if use_ref else "; oracle port, wall clock"))
+
+
+def cpu_join_once(oracle, R, S, wl, nthreads: int, use_ref: bool):
+    """one join of the reference's CPU implementation; returns (seconds, result dict)"""
+    r, s, q, variant, m, k, B, _ = wl
+    if use_ref:
+        res = oracle.ref_join(R, S, "PRO", nthreads, variant is not None, variant or 0, m or 8, k, B or 512)
+        return res["total_usecs"] * 1e-6, res
+    t0 = time.perf_counter()
+    res = oracle.join(R, S, variant is not None, variant or 0, m or 8, k, B or 512)
+    return time.perf_counter() - t0, res
 
 
 def run_reference_arm(args, wl_name, wl):
+    """The reference's own CPU implementation on the box's host cores, same config as our arm. Nothing of this repo's
+    product is imported here: the inputs come from the reference's own generator (generator.c through oracle/_ref), the
+    join is the unmodified BPRO/PRO."""
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    import hwbloomradixjoin_b200 as H
-    from hwbloomradixjoin_b200 import build
-    build.build_library()
-    H.set_quiet(True)
+    import oracle
+    use_ref = oracle.ref_available()
     nthreads = os.cpu_count() or 1
-    scale = args.ref_scale
-    total = args.steps + args.warmup
-    out = cpu_reference_sample(wl, scale, nthreads, H, reps=total)
-    times = out["times"][args.warmup:]
+    swl = scaled(wl, args.ref_scale)
+    r, s, q, variant, m, k, B, _ = swl
+    if use_ref:  # main.c:410-466 with the CLI's default seeds
+        R = oracle.ref_generate(0, r, r, 1.0, 0.0, 12345, nthreads)
+        S = oracle.ref_generate(2 if q < 0 else 1, s, r, q if q >= 0 else 1.0, -q if q < 0 else 0.0, 54321, nthreads)
+    else:
+        R, S = oracle.gen_R(r), (oracle.gen_zipf(s, r, -q) if q < 0 else oracle.gen_S(s, r, q))
+    times, res = [], None
+    for _ in range(args.steps + args.warmup):
+        t, res = cpu_join_once(oracle, R, S, swl, nthreads, use_ref)
+        times.append(t)
+    times = times[args.warmup:]
     secs = sum(times)
-    value = out["tuples"] * len(times) / secs / 1e6
+    value = (r + s) * len(times) / secs / 1e6
+    sample = sample_text(swl, args.ref_scale, use_ref)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / len(times) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": wl[7], "name": wl_name, "sample": out["sample"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": out["cores"], "kind": out["kind"],
-                             "sample": out["sample"]},
+            "config": wl_config(wl_name, wl), "sample": sample,
+            "results": {"matches": int(res["matches"]), "filtered": int(res["filtered"])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads if use_ref else 1,
+                             "kind": "reference" if use_ref else "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -212,7 +230,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-scale", type=int, default=4, help="the CPU arm runs on 1/ref-scale of the workload")
+    ap.add_argument("--ref-scale", type=int, default=1, help="the CPU arm runs on 1/ref-scale of the workload (1 = the same config)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps,5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -283,6 +301,11 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes // max(stats[-1]["range_passes"] if bloom is not None else 1, 1),
                 "note": "achieved = algorithmic bytes of the kernel's launches in one step / their summed CUDA-event time; traffic = ncu DRAM bytes of ONE launch",
                 "launches_per_step": stats[-1]["range_passes"] if bloom is not None else 1,
+                # what actually bounds K2 on this part: one divergent L1TEX access per SM per clock
+                "secondary": None if bloom is None else {
+                    "bound": "l1tex divergent accesses (1 per SM per clock = 148 x 1.965 GHz)", "unit": "G probes/s",
+                    "achieved": s * max(k, 1) / (dom_ms * 1e-3) / 1e9 if variant == 0 and k <= 1 else None,
+                    "peak": 148 * 1.965, "note": "first probes only; every key probes once per join, in the range pass of its bit"},
                 "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak}}
 
@@ -321,30 +344,43 @@ def main():
     e2e = {"value": (r + s) / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(st.h2d_bytes),
            "d2h_bytes_per_step": int(st.d2h_bytes), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
            "ms_h2d": st.ms_h2d, "api": "BPRO(relation_t*,relation_t*,int,bloom_filter_args_t*)" if bloom else "PRO(...)"}
+    # ---- CPU baseline beside it: the unmodified reference on the host cores, on the SAME arrays the host-buffer leg
+    # just joined (rank 0, N=1 only; one join of the full workload unless --ref-scale says otherwise) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            import oracle
+            use_ref = oracle.ref_available()
+            nthreads = os.cpu_count() or 1
+            sc = args.ref_scale
+            swl = scaled(wl, sc)
+            hRa = np.ctypeslib.as_array(C.cast(hR, C.POINTER(C.c_int64)), shape=(r,)).view(oracle.TUPLE)
+            hSa = np.ctypeslib.as_array(C.cast(hS, C.POINTER(C.c_int64)), shape=(s,)).view(oracle.TUPLE)
+            if sc == 1:
+                Rc, Sc = hRa, hSa
+            else:  # a smaller sample needs its own key multiset (the restated reference generator)
+                Rc = oracle.gen_R(swl[0])
+                Sc = oracle.gen_zipf(swl[1], swl[0], -q) if q < 0 else oracle.gen_S(swl[1], swl[0], q)
+            secs, cres = cpu_join_once(oracle, Rc, Sc, swl, nthreads, use_ref)
+            cpu = {"value": (swl[0] + swl[1]) / secs / 1e6, "unit": UNIT, "cores": nthreads if use_ref else 1,
+                   "kind": "reference" if use_ref else "port", "sample": sample_text(swl, sc, use_ref), "seconds": secs,
+                   "same_arrays_as_gpu": sc == 1}
+            if sc == 1:  # same arrays, so the scalars must agree
+                cpu["matches_equal"] = int(cres["matches"]) == int(res.totalresults)
+                cpu["filtered_equal"] = bloom is None or int(cres["filtered"]) == int(res.filtered)
+        except Exception as exc:  # the baseline is a reported side number: never lose the bench line over it
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {exc}"}
     L.hwbrj_host_free(hR)
     L.hwbrj_host_free(hS)
     dR.free()
     dS.free()
 
-    # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only) ----
-    cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            nthreads = os.cpu_count() or 1
-            out = cpu_reference_sample(wl, args.ref_scale, nthreads, H, reps=1)
-            cpu = {"value": out["tuples"] / out["times"][0] / 1e6, "unit": UNIT, "cores": out["cores"],
-                   "kind": out["kind"], "sample": out["sample"], "seconds": out["times"][0]}
-        except Exception as exc:  # the baseline is a reported side number: never lose the bench line over it
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {exc}"}
-
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q if q >= 0 else None, "zipf": -q if q < 0 else None,
-                       "bloom": None if bloom is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
-                       "radix_bits": stats[-1]["radix_bits"], "range_passes": stats[-1]["range_passes"],
-                       "l2": f"inputs are {((r + s) * 8) >> 20} MiB per step, larger than the 126 MB L2; no flush needed",
-                       "timed_region": "CUDA events on the library stream around every launch of the join, filter/histogram zero-fill included"},
+            "config": wl_config(args.workload, wl),
+            "details": {"radix_bits": stats[-1]["radix_bits"], "range_passes": stats[-1]["range_passes"],
+                        "timed_region": "CUDA events on the library stream around every launch of the join, filter/histogram zero-fill included"},
             "results": {"matches": res.totalresults, "filtered": res.filtered, "checksum_pair": res.checksum_pair},
             "phases_ms": phases, "wall_ms_per_step": wall / args.steps * 1e3,
             "ms_per_step_without_zero_fill": ms_per_step - phases["ms_memset"],  # the reference's own timed region (:1583)

@@ -38,7 +38,8 @@ class StatsT(C.Structure):  # hwbrj_stats_t
                 ("ms_probe", C.c_float), ("ms_part_s", C.c_float), ("ms_join", C.c_float), ("ms_h2d", C.c_float),
                 ("ms_e2e", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_int32), ("radix_bits", C.c_int32), ("range_passes", C.c_int32),
-                ("n_gpus", C.c_int32), ("ms_comm", C.c_float), ("reserved", C.c_float * 3)]
+                ("n_gpus", C.c_int32), ("ms_comm", C.c_float), ("reserved", C.c_float * 3),
+                ("owned_r", C.c_uint64), ("owned_s", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -46,14 +47,17 @@ class StatsT(C.Structure):  # hwbrj_stats_t
 
 # every symbol include/hwbrj.h declares (tests check that the library exports all of them)
 EXPORTS = ["BPRO", "BRJ", "BPRH", "BPRHO", "PRO", "RJ", "PRH", "PRHO", "hwbrj_last_stats", "hwbrj_last_filtered",
-           "hwbrj_last_checksum", "hwbrj_last_filter", "hwbrj_set_quiet", "hwbrj_set_radix_bits", "hwbrj_set_range_passes", "hwbrj_set_overlap_h2d", "hwbrj_set_hash_partition", "hwbrj_version",
+           "hwbrj_last_checksum", "hwbrj_last_filter", "hwbrj_set_quiet", "hwbrj_set_radix_bits", "hwbrj_set_num_passes",
+           "hwbrj_set_range_passes", "hwbrj_set_gpus", "hwbrj_set_overlap_h2d", "hwbrj_set_hash_partition", "hwbrj_version",
            "hwbrj_device_count", "hwbrj_check_args", "hwbrj_rel_upload", "hwbrj_rel_generate", "hwbrj_rel_download",
-           "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_join_device_async", "hwbrj_join_prepare_r", "hwbrj_host_alloc", "hwbrj_host_free",
-           "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_fpr_count", "hwbrj_materialize_last", "hwbrj_materialize_last_device", "hwbrj_radix_partition",
-           "hwbrj_set_stream", "hwbrj_reset_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr", "hwbrj_rel_generate_shard",
-           "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe",
-           "hwbrj_rel_wrap_counted", "hwbrj_symm_alloc", "hwbrj_symm_free", "hwbrj_ipc_export", "hwbrj_ipc_open",
-           "hwbrj_ipc_close", "hwbrj_route_peer", "hwbrj_filter_probe_async"]
+           "hwbrj_rel_size", "hwbrj_rel_free", "hwbrj_join_device", "hwbrj_join_device_async", "hwbrj_host_alloc",
+           "hwbrj_host_free", "hwbrj_hash_many", "hwbrj_bloom_build", "hwbrj_bloom_probe", "hwbrj_fpr_count",
+           "hwbrj_materialize_last", "hwbrj_materialize_last_device", "hwbrj_radix_partition",
+           "hwbrj_dist_create", "hwbrj_dist_connect", "hwbrj_dist_join", "hwbrj_dist_join_async", "hwbrj_dist_filter",
+           "hwbrj_dist_destroy",
+           "hwbrj_set_stream", "hwbrj_reset_stream", "hwbrj_sync", "hwbrj_set_device", "hwbrj_rel_wrap", "hwbrj_rel_ptr",
+           "hwbrj_rel_generate_shard", "hwbrj_owner_partition", "hwbrj_filter_build", "hwbrj_filter_or", "hwbrj_filter_probe"]
+DIST_HANDLE_BYTES = 128  # HWBRJ_DIST_HANDLE_BYTES
 
 _lib = None
 
@@ -85,6 +89,8 @@ def load():
     L.hwbrj_set_quiet.argtypes = [C.c_int]
     L.hwbrj_set_radix_bits.argtypes = [C.c_int]
     L.hwbrj_set_range_passes.argtypes = [C.c_int]
+    L.hwbrj_set_num_passes.argtypes = [C.c_int]
+    L.hwbrj_set_gpus.argtypes = [C.c_int]
     L.hwbrj_set_hash_partition.argtypes = [C.c_int]
     L.hwbrj_set_overlap_h2d.argtypes = [C.c_int]
     L.hwbrj_version.restype = C.c_char_p
@@ -99,8 +105,14 @@ def load():
     L.hwbrj_rel_free.argtypes = [C.c_void_p]
     L.hwbrj_join_device.argtypes = [C.c_void_p, C.c_void_p, argp, C.POINTER(StatsT)]
     L.hwbrj_join_device_async.argtypes = [C.c_void_p, C.c_void_p, argp, C.c_void_p]
-    L.hwbrj_join_prepare_r.restype = C.c_int
-    L.hwbrj_join_prepare_r.argtypes = [C.c_void_p]
+    L.hwbrj_dist_create.restype = C.c_void_p
+    L.hwbrj_dist_create.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.hwbrj_dist_connect.argtypes = [C.c_void_p, C.c_char_p]
+    L.hwbrj_dist_join.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, argp, C.c_uint64, C.POINTER(StatsT)]
+    L.hwbrj_dist_join_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, argp, C.c_uint64, C.c_void_p]
+    L.hwbrj_dist_filter.restype = C.c_void_p
+    L.hwbrj_dist_filter.argtypes = [C.c_void_p]
+    L.hwbrj_dist_destroy.argtypes = [C.c_void_p]
     L.hwbrj_host_alloc.restype = C.c_void_p
     L.hwbrj_host_alloc.argtypes = [C.c_uint64]
     L.hwbrj_host_free.argtypes = [C.c_void_p]
@@ -119,17 +131,6 @@ def load():
     L.hwbrj_set_device.argtypes = [C.c_int]
     L.hwbrj_rel_wrap.restype = C.c_void_p
     L.hwbrj_rel_wrap.argtypes = [C.c_void_p, C.c_uint64]
-    L.hwbrj_rel_wrap_counted.restype = C.c_void_p
-    L.hwbrj_rel_wrap_counted.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
-    L.hwbrj_symm_alloc.restype = C.c_void_p
-    L.hwbrj_symm_alloc.argtypes = [C.c_uint64]
-    L.hwbrj_symm_free.argtypes = [C.c_void_p]
-    L.hwbrj_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
-    L.hwbrj_ipc_open.restype = C.c_void_p
-    L.hwbrj_ipc_open.argtypes = [C.c_void_p]
-    L.hwbrj_ipc_close.argtypes = [C.c_void_p]
-    L.hwbrj_route_peer.argtypes = [C.c_void_p, C.c_int, argp, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-    L.hwbrj_filter_probe_async.argtypes = [C.c_void_p, C.c_void_p, argp, C.c_void_p, C.c_void_p]
     L.hwbrj_rel_ptr.restype = C.c_void_p
     L.hwbrj_rel_ptr.argtypes = [C.c_void_p]
     L.hwbrj_rel_generate_shard.restype = C.c_void_p

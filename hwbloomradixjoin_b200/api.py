@@ -164,6 +164,17 @@ def set_range_passes(passes: int) -> None:
     N.load().hwbrj_set_range_passes(int(passes))
 
 
+def set_num_passes(passes: int) -> None:
+    """NUM_PASSES of the reference (prj_params.h:20-22) at run time: 1 or 2 scatter passes, 0 = automatic"""
+    N.load().hwbrj_set_num_passes(int(passes))
+
+
+def set_gpus(n: int) -> None:
+    """host-buffer joins (BPRO, PRO, ...) shard over the first n GPUs of this process"""
+    if N.load().hwbrj_set_gpus(int(n)) != 0:
+        raise ValueError(f"cannot use {n} GPUs (power of two, at most the device count)")
+
+
 def set_hash_partition(mode: int) -> None:
     """0 never, 1 automatic (filters > 32 MiB), 2 whenever possible"""
     N.load().hwbrj_set_hash_partition(int(mode))

@@ -1,13 +1,16 @@
 """bench.py's N>1 arm: launched by torchrun with one rank per GPU (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* from the
 environment). Strong scaling: the BASELINE workload is split into contiguous chunks over the ranks; `value` is
-(|R|+|S|) over the max-over-ranks device time of the collective join, inputs resident in HBM."""
+(|R|+|S|) over the max-over-ranks device time of the collective join, inputs resident in HBM.
+
+torch is the launcher here: process group for the start-up handle exchange and the max-over-ranks reductions of the
+timings, CUDA events and the CUDA graph. The join itself -- kernels, NVLink peer stores, device-side barriers -- is one
+call into the library per rank (hwbrj_dist_join / hwbrj_dist_join_async)."""
 from __future__ import annotations
 
 import json
 import os
 import sys
 import threading
-import statistics
 import time
 
 import torch
@@ -32,13 +35,13 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
     from . import BloomFilterArgs
-    from .dist import CudaOps, PeerFabric, PeerJoinGraph, dist_join, dist_join_peer
+    from .dist import CudaOps, DistGroup, DistJoinGraph, dist_join
     ops = CudaOps(device)
     r, s, q, variant, m, k, B, desc = wl
     bloom = BloomFilterArgs(variant, m, k, B) if variant is not None else None
 
     def chunk(n):
-        per = n // world
+        per = (n // world) & ~1  # even chunk starts keep every chunk 16-byte aligned
         lo = rank * per
         return lo, (n - lo if rank == world - 1 else per)
     rlo, rcnt = chunk(r)
@@ -46,32 +49,35 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     Rsh = ops.generate_shard(0, r, r, 1.0, 1, rlo, rcnt)
     Ssh = ops.generate_shard(2 if q < 0 else 1, s, r, -q if q < 0 else q, 2, slo, scnt)  # q < 0: Zipf exponent -q
 
-    # exchanges fused into the partitioning kernels (NVLink peer stores); NCCL all-to-all is the fallback
-    use_peer = os.environ.get("HWBRJ_DIST_PATH", "peer") == "peer"
-    fabric = None
-    if use_peer:
-        try:  # the constructor fails on ALL ranks together when peer memory cannot be mapped -> NCCL all-to-all path
-            # receive capacity per rank: 20 % over the even share; a Zipf probe relation sends its hot keys (all of
-            # them survive the filter) to single owners, so leave 2.5x there (overflow falls back to NCCL anyway)
-            s_slack = 2.5 if q < 0 else 1.2
-            fabric = PeerFabric(ops, int(r / world * 1.2) + 65536, int(s / world * s_slack) + 65536)
-        except Exception as exc:
-            print(f"[bench] NVLink peer path unavailable ({exc}); using NCCL all-to-all", flush=True)
+    def allmax(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
 
-    def step(Rt, St, time_phases=False):
-        if fabric is not None:
-            out = dist_join_peer(ops, fabric, Rt, St, bloom, r, s, time_phases=time_phases)
+    # The GPU group: receive buffers sized for 25 % imbalance of R (hash owners of distinct keys) and for the worst case
+    # of the probe side (every S tuple survives and one owner gets them all: a Zipf hot key), so nothing can overflow.
+    use_peer = os.environ.get("HWBRJ_DIST_PATH", "peer") == "peer"
+    grp = None
+    if use_peer:
+        try:  # fails on ALL ranks together when peer memory cannot be mapped -> NCCL reference path
+            grp = DistGroup(ops, int(r / world * 1.25) + 65536, s + 2, max(m // 8, 16) if bloom is not None else 16)
+        except Exception as exc:
+            print(f"[bench] NVLink peer path unavailable ({exc}); using the NCCL all-to-all path", flush=True)
+
+    def step(Rt, St):
+        if grp is not None:
+            out = grp.join(Rt, St, bloom, r)
             if out is not None:
                 return out
-        out = dist_join(ops, Rt, St, bloom, time_phases=time_phases)
+        out = dist_join(ops, Rt, St, bloom)
         out["path"] = "nccl-all-to-all"
         return out
 
-    # device-resident leg: the whole collective join replayed as one CUDA graph (kernels + NVLink stores + NCCL)
+    # device-resident leg: the whole collective join replayed as one CUDA graph
     graph = None
-    if fabric is not None and os.environ.get("HWBRJ_DIST_GRAPH", "1") == "1":
+    if grp is not None and os.environ.get("HWBRJ_DIST_GRAPH", "1") == "1":
         try:
-            graph = PeerJoinGraph(ops, fabric, Rsh, Ssh, bloom, r, s)
+            graph = DistJoinGraph(grp, Rsh, Ssh, bloom, r)
             if graph.replay() is None:
                 graph = None
         except Exception as exc:  # capture not possible here: run the eager pipeline
@@ -104,11 +110,28 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     dist.barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
-    ms_per_step = ms.item() / args.steps
+    ms_per_step = allmax(ev0.elapsed_time(ev1)) / args.steps
     value = (r + s) / (ms_per_step * 1e-3) / 1e6
-    phased = step(Rsh, Ssh, time_phases=True)
+
+    # per-phase device times and per-GPU load: eager joins (the library's own CUDA events on its stream), mean over the
+    # steps, max over the ranks; the ranks run in lock step because every phase boundary that matters is a device barrier
+    phases, loads = {}, None
+    if grp is not None:
+        acc = {}
+        n_eager = min(args.steps, 5)
+        for _ in range(n_eager):
+            e = step(Rsh, Ssh)
+            for kk, vv in e["local"].items():
+                if kk.startswith("ms_"):
+                    acc[kk] = acc.get(kk, 0.0) + vv / n_eager
+        phases = {kk: allmax(vv) for kk, vv in sorted(acc.items())}
+        t = torch.zeros(2 * world, dtype=torch.int64, device=device)
+        t[2 * rank], t[2 * rank + 1] = e["owned_r"], e["owned_s"]
+        dist.all_reduce(t)
+        loads = {"owned_r_per_gpu": t[0::2].tolist(), "owned_s_per_gpu": t[1::2].tolist()}
+        launches = e["local"]["kernel_launches"]
+    else:
+        launches = res.get("local", {}).get("kernel_launches", 0) + 8
 
     # ---- host-buffer leg: pinned host shards -> device, collective join, scalars back ----
     e2e_steps = args.e2e_steps or min(args.steps, 5)
@@ -129,41 +152,47 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     for _ in range(e2e_steps):
         hres = host_step()
     torch.cuda.synchronize()
-    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
-    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
     assert hres["matches"] == res["matches"]
 
     if rank == 0:
         peak, peak_src = measured_peak()
         F = res["filtered"] if bloom is not None else s
         b_alg = (24 * r + 8 * s + 16 * F + 2 * (m // 8)) if bloom is not None else (24 * r + 24 * s)
-        ph = phased.get("phases_ms", {})
-        probe_ms = ph.get("s_probe")
-        roofline = {"bound": "hbm", "kernel": "k_probe_compact (K2) on the rank's S chunk", "unit": "GB/s",
+        probe_ms = phases.get("ms_probe") if bloom is not None else None
+        roofline = {"bound": "hbm", "kernel": "k_probe_compact (K2) on every rank's S chunk", "unit": "GB/s",
                     "peak": peak * world, "peak_source": peak_src + f" x {world} GPUs",
+                    # every rank reads its S chunk, writes its survivors and reads the whole replicated filter
                     "achieved": (8 * s + 8 * F + world * (m // 8)) / (probe_ms * 1e-3) / 1e9 if probe_ms else None,
                     "traffic": None,
+                    "note": "phase times: mean of eager joins, library CUDA events, max over ranks; whole_join from graph replays",
                     "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,
                                    "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / (peak * world)}}
         if roofline["achieved"]:
             roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        moved = (r + F) * (world - 1) // world  # hash owners: (G-1)/G of R and of the survivors leave their rank
-        nvl_bytes = 8 * moved + (world - 1) * (m // 8 if bloom is not None else 0) * (1 if res["sliced_filter"] else world)
+        # NVLink: (G-1)/G of R and of the survivors leave their rank; every rank stores its filter slice into G-1 peers
+        moved = (r + F) * (world - 1) // world
+        filt_bytes = (world - 1) * (m // 8) if bloom is not None else 0
+        nvl_bytes = 8 * moved + filt_bytes
+        nvlink = {"bytes_total_per_step": nvl_bytes, "bytes_per_gpu_per_step": nvl_bytes // world,
+                  "gbps_per_gpu_over_whole_step": nvl_bytes / world / (ms_per_step * 1e-3) / 1e9,
+                  "frac_of_900_GBps_per_direction": nvl_bytes / world / (ms_per_step * 1e-3) / 1e9 / 900.0}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": desc, "name": args.workload, "r": r, "s": s, "q": q if q >= 0 else None, "zipf": -q if q < 0 else None,
                            "bloom": None if bloom is None else {"variant": "basic" if variant == 0 else "blocked", "m": m, "k": k, "B": B},
-                           "sharding": "contiguous chunks per rank; owner = filter-slice rank" if res["sliced_filter"] else "contiguous chunks per rank; owner = crapwow top bits",
+                           "sharding": "contiguous input chunks per rank; a key's owner = high bits of its partition id "
+                                       "(the rank holding its filter slice)",
                            "exchange": res.get("path", "nccl-all-to-all"),
                            "l2": "per-rank inputs exceed the 126 MB L2; no flush needed"},
                 "results": {"matches": res["matches"], "filtered": res["filtered"], "checksum_pair": res["checksum_pair"]},
-                "phases_ms_rank0": ph, "wall_ms_per_step": wall / args.steps * 1e3, "nvlink_bytes_total": nvl_bytes,
-                "roofline": roofline, "cpu_baseline": None,
-                "e2e": {"value": (r + s) / e2e_t.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (r + s),
-                        "d2h_bytes_per_step": 8 * 16 * world, "ms_per_step": e2e_t.item() * 1e3, "steps": e2e_steps,
-                        "api": "hwbloomradixjoin_b200.dist.dist_join on pinned host shards"},
-                "gpu_launches": int(args.steps * world * (phased["local"]["kernel_launches"] + 8)), "clocks": clocks,
+                "phases_ms_max_over_ranks": phases, "per_gpu_load": loads, "wall_ms_per_step": wall / args.steps * 1e3,
+                "nvlink": nvlink, "roofline": roofline, "cpu_baseline": None,
+                "e2e": {"value": (r + s) / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (r + s),
+                        "d2h_bytes_per_step": 8 * 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                        "api": "hwbrj_dist_join (C ABI) on chunks copied from pinned host memory"},
+                "gpu_launches": int(args.steps * world * launches), "clocks": clocks,
                 "cuda_graph": graph is not None}
         os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     # No collective teardown: every rank has passed the last all-reduce, rank 0 has printed its line. Tearing down the

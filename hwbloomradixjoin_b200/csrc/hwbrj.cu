@@ -1,8 +1,10 @@
-// hwbrj.cu -- host side of libhwbrj_cuda.so: workspace, the single-GPU join pipeline and the C ABI of
-// include/hwbrj.h. Mirrors the reference's join_init_run()/prj_thread() orchestration
-// (parallel_radix_join_bloom.c:1060-1506,1561-1778) as one CUDA stream of kernels with no host round trip
-// between phases; the pthread barriers of the reference become kernel boundaries.
+// hwbrj.cu -- host side of libhwbrj_cuda.so: workspace, the join pipeline (one GPU, or G GPUs of one NVLink domain)
+// and the C ABI of include/hwbrj.h. Mirrors the reference's join_init_run()/prj_thread() orchestration
+// (parallel_radix_join_bloom.c:1060-1506,1561-1778) as one CUDA stream of kernels per GPU with no host round trip
+// between phases; the pthread barriers of the reference become kernel boundaries (one GPU) or peer-memory barriers
+// (k_barrier) between the GPUs, which play the role of the reference's worker threads.
 #include <cuda_runtime.h>
+#include <unistd.h>
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
@@ -35,11 +37,14 @@ namespace hwbrj {
         if (e_ != cudaSuccess) die("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+static void invalidate_last();
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes) {
         if (bytes <= cap) return;
+        invalidate_last();  // a re-allocation may free partitions a later hwbrj_materialize_last would read
         if (p) CK(cudaFree(p));
         size_t want = bytes + (bytes >> 4) + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -53,22 +58,29 @@ struct DevBuf {
     }
     template <typename T>
     T* as() const { return reinterpret_cast<T*>(p); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
 };
 
 // small control block living in one allocation (zeroed with one memset per join)
 struct Control {
-    unsigned long long survivors;  // K2 output cursor == filtered
-    unsigned long long defer[7];   // sizes of the deferred inputs of range passes 1..7
+    unsigned long long survivors;  // K2 output cursor == filtered (this rank's S chunk)
+    unsigned long long n_own_r, n_own_s;  // tuples this rank owns after the level-1 routing
     JoinAccum acc;
     uint32_t item_counter;
-    uint32_t pad[3];
+    uint32_t abort;  // a receive buffer would overflow: the scatter kernels write nothing
+    uint32_t err;    // barrier time-out
+    uint32_t pad;
     unsigned long long pair_cursor;  // materialised output pairs
-    unsigned long long pad2;
+    unsigned long long row[8];       // this rank's result words {matches, cpair, crpay, cspay, ckey, survivors, flags, 0}
+    unsigned long long out[8];       // summed over the ranks
+};
+
+// what the pipeline needs to know about the GPUs that take part: for one GPU it points into the plain workspace
+struct Fab {
+    int world = 1, rank = 0, gbits = 0;
+    PeerPtrs flags, histR, histS, rows, filter, partial;
+    PeerBufs recvR, recvS;
+    uint32_t* epoch = nullptr;
+    uint64_t cap_r = 0, cap_s = 0, filter_bytes = 0;
 };
 
 struct Ctx {
@@ -78,12 +90,9 @@ struct Ctx {
     int clock_khz = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[12];
     uint32_t* d_crc = nullptr;
-    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, work_part, ctrl, rt1, rp, sc, st1, inR, inS, scratch;
-    DevBuf cur1b, cur2b, tilesb;          // second set of scatter cursors: R partitioning may overlap the S probe
-    cudaStream_t side_stream = nullptr;   // R partitioning runs here while K2 runs on the main stream
-    cudaEvent_t ev_side[4];
+    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, work_part, ctrl, rt1, rp, sc, st1, s2, inR, inS, scratch;
     // state of the most recent join's partitions (inputs of a materialising k_join pass)
     const uint2* last_Rp = nullptr;
     const uint2* last_Sp = nullptr;
@@ -93,49 +102,63 @@ struct Ctx {
     // host-buffer calls: upload S in chunks on a copy stream and probe each chunk as soon as it has landed
     bool overlap_h2d = false;
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2];
     cudaEvent_t ev_chunk[66];
-    bool hash_partition = true;           // BASIC k<=1: partition on the filter-slice index, build the filter in smem
-    bool hash_partition_force = false;    // HWBRJ_HASH_PARTITION=2: also for small filters (tests)
-    bool overlap_r_partition = false;     // measured: the scatter traffic evicts the probed filter range (C1: 11.1 vs 9.9 ms)
+    int hash_partition = 1;  // 0 never, 1 automatic, 2 whenever the slices fit (see pick_mode)
     hwbrj_stats_t last;
-    bool quiet = false;
     int radix_bits_override = 0;
+    int passes_override = 0;
     int range_passes_override = 0;
-    int probe_ctas_per_sm = 0;  // 0 = occupancy API
+    int probe_ctas_per_sm = 0;  // 0 = min(occupancy, 4)
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
-    bool probe_staged = false;  // experimental: k >= 2 probes run on compacted candidates (k_probe_staged)
-    // R side of a filter-less join partitioned ahead of time on the side stream (hwbrj_join_prepare_r)
-    struct {
-        bool valid = false;
-        const uint2* d = nullptr;
-        uint64_t n = 0;
-        const unsigned long long* n_dev = nullptr;
-        int bits = 0;
-        const uint2* Rp = nullptr;
-        int launches = 0;
-    } prep;
-    cudaEvent_t ev_prep_fork = nullptr, ev_prep_done = nullptr;
-    bool route_precount = false;  // experimental: hwbrj_route_peer claims once per owner (k_route_claim)
-    DevBuf route_hist, route_cur;
-    DevBuf histF;  // one-bin histogram of filter-only builds while histR belongs to a prepared R partitioning
-    bool defer_ranges = false;  // range passes with deferral: measured slower on B200 (deferred writes thrash L2), kept as an option
-    DevBuf d1;                  // second deferral buffer (only for more than 2 range passes)
+    bool probe_staged = false;  // k >= 2 probes run on compacted candidates (k_probe_staged)
     DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
     uint64_t zipf_r = 0;
     double zipf_theta = -1.0;
-    int occ_scatter1 = 1, occ_scatter2 = 1, occ_join = 1;
-    std::mutex mu;
+    int occ_scatter = 1, occ_join = 1, occ_probe[8] = {0}, occ_staged = 1;
 };
 
-static Ctx g;
+static Ctx g_ctx[kMaxPeers];  // one context per device of this process (one process per GPU uses exactly one)
+static Ctx* g_cur = nullptr;
+#define g (*g_cur)
+static std::recursive_mutex g_mu;
+static bool g_quiet = false;
+static int g_gpus = 1;  // hwbrj_set_gpus: the host-buffer entry points shard over this many GPUs of the process
+
+static void invalidate_last() {
+    if (g_cur) g.last_Rp = g.last_Sp = nullptr;
+}
+
+template <typename K>
+static void set_smem(K kernel, int bytes) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
+constexpr int kHistSmem = ((1 << kMaxRadixBits) + kCrcSmemWords) * 4;
+constexpr int kFilterSliceSmemMax = 192 * 1024;
+
+template <int M>
+static void init_probe_mode() {
+    const int smem = kProbeWarps * kProbeSmemPerWarp;
+    set_smem(k_probe_compact<M>, smem);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_probe[M], k_probe_compact<M>, kProbeWarps * 32, smem));
+    g.occ_probe[M] = std::max(g.occ_probe[M], 1);
+    if (g.probe_carveout >= 0)
+        CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributePreferredSharedMemoryCarveout, g.probe_carveout));
+}
 
 static void init_ctx() {
-    if (g.inited) return;
+    std::lock_guard<std::recursive_mutex> lock(g_mu);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         die("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
-    CK(cudaGetDevice(&g.dev));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev >= kMaxPeers) die("device ordinal %d not supported", dev);
+    g_cur = &g_ctx[dev];  // the current CUDA device selects the context
+    if (g.inited) return;
+    g.dev = dev;
     cudaDeviceProp pr;
     CK(cudaGetDeviceProperties(&pr, g.dev));
     g.sms = pr.multiProcessorCount;
@@ -143,49 +166,41 @@ static void init_ctx() {
     CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
-    CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : g.ev_copy) CK(cudaEventCreate(&ev));
     for (auto& ev : g.ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    if (const char* s = getenv("HWBRJ_OVERLAP_H2D")) g.overlap_h2d = atoi(s) != 0;
-    for (auto& ev : g.ev_side) CK(cudaEventCreate(&ev));
-    CK(cudaEventCreateWithFlags(&g.ev_prep_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&g.ev_prep_done, cudaEventDisableTiming));
-    if (const char* s = getenv("HWBRJ_OVERLAP")) g.overlap_r_partition = atoi(s) != 0;
     CrcTables T;
     crc_tables_fill(T);
     CK(cudaMalloc(&g.d_crc, sizeof(T)));
     CK(cudaMemcpy(g.d_crc, &T, sizeof(T), cudaMemcpyHostToDevice));
-    const int hist_smem = ((1 << kMaxRadixBits) + kCrcSmemWords) * 4;
-    CK(cudaFuncSetAttribute(k_build_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    CK(cudaFuncSetAttribute(k_build_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    CK(cudaFuncSetAttribute(k_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
-    CK(cudaFuncSetAttribute(k_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
-    CK(cudaFuncSetAttribute(k_join<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
-    CK(cudaFuncSetAttribute(k_join<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJoinSmemBytes));
+    if (const char* s = getenv("HWBRJ_OVERLAP_H2D")) g.overlap_h2d = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_RADIX_BITS")) g.radix_bits_override = atoi(s);
+    if (const char* s = getenv("HWBRJ_NUM_PASSES")) g.passes_override = atoi(s);
     if (const char* s = getenv("HWBRJ_RANGE_PASSES")) g.range_passes_override = atoi(s);
-    if (const char* s = getenv("HWBRJ_QUIET")) g.quiet = atoi(s) != 0;
+    if (const char* s = getenv("HWBRJ_QUIET")) g_quiet = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_CARVEOUT")) g.probe_carveout = std::min(100, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_STAGED")) g.probe_staged = atoi(s) != 0;
-    if (const char* s = getenv("HWBRJ_ROUTE_PRECOUNT")) g.route_precount = atoi(s) != 0;
-    if (const char* s = getenv("HWBRJ_DEFER")) g.defer_ranges = atoi(s) != 0;
-    CK(cudaFuncSetAttribute(k_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-    CK(cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-    CK(cudaFuncSetAttribute(k_scatter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-    CK(cudaFuncSetAttribute(k_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-    CK(cudaFuncSetAttribute(k_scatter<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-    CK(cudaFuncSetAttribute(k_filter_from_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
-    CK(cudaFuncSetAttribute(k_build_hist<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
-    if (const char* s = getenv("HWBRJ_HASH_PARTITION")) {
-        g.hash_partition = atoi(s) != 0;
-        g.hash_partition_force = atoi(s) == 2;
-    }
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter1, k_scatter<1>, kScatterThreads, kScatterSmem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter2, k_scatter<2>, kScatterThreads, kScatterSmem));
+    if (const char* s = getenv("HWBRJ_HASH_PARTITION")) g.hash_partition = std::max(0, std::min(2, atoi(s)));
+    // kernel attributes are per device: every instantiation the pipeline can launch is prepared here
+    set_smem(k_build_hist<false, 0>, kHistSmem); set_smem(k_build_hist<false, 1>, kHistSmem);
+    set_smem(k_build_hist<false, 2>, kHistSmem); set_smem(k_build_hist<true, 0>, kHistSmem);
+    set_smem(k_scatter<1, 0, false>, kScatterSmem); set_smem(k_scatter<1, 1, false>, kScatterSmem);
+    set_smem(k_scatter<1, 2, false>, kScatterSmem); set_smem(k_scatter<1, 0, true>, kScatterSmem);
+    set_smem(k_scatter<1, 1, true>, kScatterSmem);  set_smem(k_scatter<1, 2, true>, kScatterSmem);
+    set_smem(k_scatter<2, 0, false>, kScatterSmem); set_smem(k_scatter<2, 1, false>, kScatterSmem);
+    set_smem(k_scatter<2, 2, false>, kScatterSmem);
+    set_smem(k_filter_from_parts<false, false>, kFilterSliceSmemMax); set_smem(k_filter_from_parts<false, true>, kFilterSliceSmemMax);
+    set_smem(k_filter_from_parts<true, false>, kFilterSliceSmemMax);  set_smem(k_filter_from_parts<true, true>, kFilterSliceSmemMax);
+    set_smem(k_join<false>, kJoinSmemBytes); set_smem(k_join<true>, kJoinSmemBytes);
+    set_smem(k_join<false, true>, kJoinSmemBytes); set_smem(k_join<true, true>, kJoinSmemBytes);
+    init_probe_mode<0>(); init_probe_mode<1>(); init_probe_mode<2>(); init_probe_mode<3>();
+    init_probe_mode<4>(); init_probe_mode<5>(); init_probe_mode<6>(); init_probe_mode<7>();
+    set_smem(k_probe_staged<0>, kProbeWarps * kProbeSmemPerWarp); set_smem(k_probe_staged<1>, kProbeWarps * kProbeSmemPerWarp);
+    set_smem(k_probe_staged<4>, kProbeWarps * kProbeSmemPerWarp); set_smem(k_probe_staged<5>, kProbeWarps * kProbeSmemPerWarp);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter, k_scatter<1, 1, false>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join<false>, kJoinThreads, kJoinSmemBytes));
-    g.occ_scatter1 = std::max(g.occ_scatter1, 1);
-    g.occ_scatter2 = std::max(g.occ_scatter2, 1);
+    g.occ_scatter = std::max(g.occ_scatter, 1);
     g.occ_join = std::max(g.occ_join, 1);
     memset(&g.last, 0, sizeof(g.last));
     g.inited = true;
@@ -246,7 +261,7 @@ static int pick_ranges(const bloom_filter_args_t* a) {
     if (a->variant == BASIC && a->k > 1) return 1;
     uint64_t bytes = a->m / 8;
     int nr = 1;
-    if (g.range_passes_override > 0) nr = g.range_passes_override;
+    if (g.range_passes_override > 0) nr = std::min(g.range_passes_override, 64);
     else
         while ((bytes / nr) > (64ull << 20)) nr <<= 1;
     // must be a power of two and leave ranges >= one block / one word
@@ -255,151 +270,157 @@ static int pick_ranges(const bloom_filter_args_t* a) {
     while (nr > 1 && a->m / nr < min_range_bits) nr >>= 1;
     return std::max(nr, 1);
 }
-
-static int pick_bits(uint64_t nR) {
-    if (g.radix_bits_override > 0) return std::min(g.radix_bits_override, (int)kMaxRadixBits);
-    int b = 0;
-    while (b < kMaxRadixBits && (nR >> b) > (uint64_t)(kTableCap * 3 / 4)) b++;
-    return b;
+static void set_ranges(BloomParams& bp, const bloom_filter_args_t* a, int nranges) {
+    bp.nranges = (uint32_t)nranges;
+    bp.range_shift = (uint32_t)(ilog2_u64(a->m) - ilog2_u64((uint64_t)nranges));
 }
 
+// total partition bits: the smallest fan-out whose R partitions fit one shared-memory table (the reference's
+// NUM_RADIX_BITS, prj_params.h:15-17, is a compile-time constant; here HWBRJ_RADIX_BITS / hwbrj_set_radix_bits override)
+static int pick_bits(uint64_t nR, int gbits) {
+    int b = 0;
+    if (g.radix_bits_override > 0) b = std::min(g.radix_bits_override, (int)kMaxRadixBits);
+    else
+        while (b < kMaxRadixBits && (nR >> b) > (uint64_t)(kTableCap * 3 / 4)) b++;
+    return std::max(b, gbits);
+}
+// level-2 bits (the reference's NUM_PASSES, prj_params.h:20-22; HWBRJ_NUM_PASSES / hwbrj_set_num_passes override):
+// one pass while the fan-out fits one scatter pass, else two passes of about equal width
+static int pick_b2(int bits, int gbits) {
+    int passes = g.passes_override;
+    if (passes == 1 && bits > kMaxLevelBits) passes = 2;  // one pass cannot exceed 2^7 bins
+    if (passes <= 0) passes = bits > kMaxLevelBits ? 2 : 1;
+    if (passes == 1 || bits < 2) return 0;
+    int b2 = std::min(bits / 2, bits - gbits);  // the owner is a prefix of the level-1 bin
+    if (bits - b2 > kMaxLevelBits) b2 = bits - kMaxLevelBits;
+    return std::max(b2, 0);
+}
 
-// K2 launch with compile-time specialisation on (blocked, k == 1, ranged, defer)
+// ---- kernel dispatch on the compile-time specialisations ---------------------------------------------------------------
+// K2 launch: (blocked, k == 1, ranged)
 static void launch_probe_mode(int mode, const uint2* in, uint64_t n, const unsigned long long* n_ptr, const BloomParams& bp,
-                              uint2* out, unsigned long long* cursor, uint2* defer_out, unsigned long long* defer_cursor) {
-    static int occ[16] = {0};
-#define HWBRJ_PROBE_CASE(M)                                                                                         \
-    case M: {                                                                                                       \
-        const int smem = kProbeWarps * kProbeSmemPerWarp(M);                                                        \
-        if (!occ[M]) {                                                                                              \
-            CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[M], k_probe_compact<M>, kProbeWarps * 32, smem)); \
-            occ[M] = std::max(occ[M], 1);                                                                           \
-            if (g.probe_carveout >= 0)                                                                              \
-                CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
-                                        g.probe_carveout));                                                         \
-        }                                                                                                           \
-        /* measured on B200: 4 CTAs/SM beats the occupancy maximum (less L2 thrash of the filter range) */          \
-        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(occ[M], 4));                 \
-        k_probe_compact<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor,     \
-                                                                       defer_out, defer_cursor);                    \
-        break;                                                                                                      \
-    }
-    if (g.probe_staged && bp.k >= 2u && !(mode & (2 | 8))) {  // experimental staged probe for k >= 2 (HWBRJ_PROBE_STAGED=1)
-        const int smem = kProbeWarps * kProbeSmemPerWarp(0);
+                              uint2* out, unsigned long long* cursor) {
+    const int smem = kProbeWarps * kProbeSmemPerWarp;
+    if (g.probe_staged && bp.k >= 2u && !(mode & 2)) {  // staged probe for k >= 2 (HWBRJ_PROBE_STAGED=1)
         const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : 4);
-#define HWBRJ_STAGED_CASE(M)                                                                                        \
-    case M: {                                                                                                       \
-        static bool attr = false;                                                                                   \
-        if (!attr) {                                                                                                \
-            CK(cudaFuncSetAttribute(k_probe_staged<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
-            attr = true;                                                                                            \
-        }                                                                                                           \
-        k_probe_staged<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor);      \
-        return;                                                                                                     \
-    }
         switch (mode) {
-            HWBRJ_STAGED_CASE(0) HWBRJ_STAGED_CASE(1) HWBRJ_STAGED_CASE(4) HWBRJ_STAGED_CASE(5)
+            case 0: k_probe_staged<0><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
+            case 1: k_probe_staged<1><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
+            case 4: k_probe_staged<4><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
+            case 5: k_probe_staged<5><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
             default: break;
         }
-#undef HWBRJ_STAGED_CASE
+    }
+    // measured on B200: 4 CTAs/SM beats the occupancy maximum (more L1 left for the loads in flight)
+#define HWBRJ_PROBE_CASE(M)                                                                                          \
+    case M: {                                                                                                        \
+        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(g.occ_probe[M], 4));          \
+        k_probe_compact<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor);      \
+        break;                                                                                                       \
     }
     switch (mode) {
         HWBRJ_PROBE_CASE(0) HWBRJ_PROBE_CASE(1) HWBRJ_PROBE_CASE(2) HWBRJ_PROBE_CASE(3)
         HWBRJ_PROBE_CASE(4) HWBRJ_PROBE_CASE(5) HWBRJ_PROBE_CASE(6) HWBRJ_PROBE_CASE(7)
-        HWBRJ_PROBE_CASE(12) HWBRJ_PROBE_CASE(13) HWBRJ_PROBE_CASE(14) HWBRJ_PROBE_CASE(15)
         default: die("bad probe mode %d", mode);
     }
 #undef HWBRJ_PROBE_CASE
 }
 
-// All range passes of the S-side probe. With deferral (default) pass i reads what pass i-1 deferred, so S itself is
-// read once; buffers d0/d1 (|S| tuples each) ping-pong. Returns the number of kernel launches.
-static int run_probe(const uint2* dS, uint64_t nS, BloomParams bp, int nranges, uint2* out, Control* ctrl, uint2* d0,
-                     uint2* d1) {
+// all range passes of the S-side probe; returns the number of kernel launches
+static int run_probe(const uint2* dS, uint64_t nS, const unsigned long long* n_ptr, BloomParams bp, int nranges, uint2* out,
+                     unsigned long long* cursor) {
     const int base_mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0);
     bp.nranges = (uint32_t)nranges;
     if (nranges == 1) {
-        launch_probe_mode(base_mode, dS, nS, nullptr, bp, out, &ctrl->survivors, nullptr, nullptr);
+        launch_probe_mode(base_mode, dS, nS, n_ptr, bp, out, cursor);
         return 1;
     }
-    const bool defer = g.defer_ranges && d0 && (nranges == 2 || d1);
-    const uint2* in = dS;
-    const unsigned long long* n_ptr = nullptr;
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        if (!defer) {
-            launch_probe_mode(base_mode | 4, dS, nS, nullptr, bp, out, &ctrl->survivors, nullptr, nullptr);
-        } else if (r + 1 < nranges) {
-            uint2* dout = (r & 1) ? d1 : d0;
-            launch_probe_mode(base_mode | 4 | 8, in, nS, n_ptr, bp, out, &ctrl->survivors, dout, &ctrl->defer[r]);
-            in = dout;
-            n_ptr = &ctrl->defer[r];
-        } else {
-            BloomParams last = bp;  // everything left belongs to the last range: no range test needed
-            last.nranges = 1;
-            launch_probe_mode(base_mode, in, nS, n_ptr, last, out, &ctrl->survivors, nullptr, nullptr);
-        }
+        launch_probe_mode(base_mode | 4, dS, nS, n_ptr, bp, out, cursor);
     }
     return nranges;
 }
 
-
-// histogram already in `hist`; runs scan + 1 or 2 scatter passes. n_dev (optional) = device-side tuple count.
-// Partition function of the join: key & (2^bits-1) (the reference's radix clustering), or -- for a BASIC k<=1 filter
-// -- the filter-slice index (crapwow(42,key) & (m-1)) >> (log2 m - bits), which lets K1' build the filter in shared memory.
-struct PartFn {
-    bool hash = false;
-    uint32_t seed = 42u, size_mask = 0u;
-    int log2m = 0;
-};
-
-static const uint2* run_partition(const uint2* in, uint64_t n, const unsigned long long* n_dev, int bits, int b2,
-                                  uint32_t* hist, uint32_t* off, uint2* t1, uint2* t2, int& launches,
-                                  cudaStream_t stream = nullptr, bool second_set = false, PartFn pf = PartFn()) {
-    if (!stream) stream = g.stream;
-    uint32_t* cur1 = second_set ? g.cur1b.as<uint32_t>() : g.cur1.as<uint32_t>();
-    uint32_t* cur2 = second_set ? g.cur2b.as<uint32_t>() : g.cur2.as<uint32_t>();
-    uint32_t* tiles = second_set ? g.tilesb.as<uint32_t>() : g.tiles.as<uint32_t>();
-    const uint32_t P = 1u << bits;
-    const uint32_t pmask = P - 1u;
-    const int b1 = bits - b2;
-    k_scan<<<1, 1024, 0, stream>>>(hist, P, (uint32_t)b2, off, cur1, cur2, tiles);
-    launches++;
-    BinFn fn;
-    memset(&fn, 0, sizeof(fn));
-    fn.pmask = pmask;
-    fn.b2 = (uint32_t)b2;
-    fn.submask = (1u << b2) - 1u;
-    if (pf.hash) {
-        fn.seed = pf.seed;
-        fn.size_mask = pf.size_mask;
-        fn.oshift = (uint32_t)(pf.log2m - b1);  // level 1: the top b1 bits of the slice index
-        fn.binmask = 0xFFFFFFFFu;
-        k_scatter<3><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, stream>>>(
-            in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off, tiles, cur1, fn, g.d_crc, 1u << b1);
-        launches++;
-        if (b2 == 0) return t1;
-        fn.oshift = (uint32_t)(pf.log2m - bits);  // level 2: the low b2 bits of the slice index
-        fn.binmask = (1u << b2) - 1u;
-        k_scatter<5><<<g.sms * g.occ_scatter2, kScatterThreads, kScatterSmem, stream>>>(t1, t2, nullptr, n, off, tiles,
-                                                                                       cur2, fn, g.d_crc, 1u << b2);
-        launches++;
-        return t2;
+static void launch_hist(int pmode, const uint2* in, uint64_t n, const unsigned long long* n_ptr, const BloomParams& bp,
+                        uint32_t* hist, const PartFn& pf) {
+    const int smem = (int)(((1u << pf.bits) + kCrcSmemWords) * 4);
+    const int grid = g.sms * 2;
+    switch (pmode) {
+        case 0: k_build_hist<false, 0><<<grid, 1024, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, hist, pf); break;
+        case 1: k_build_hist<false, 1><<<grid, 1024, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, hist, pf); break;
+        default: k_build_hist<false, 2><<<grid, 1024, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, hist, pf); break;
     }
-    k_scatter<1><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, stream>>>(
-        in, t1, reinterpret_cast<const uint64_t*>(n_dev), n, off, tiles, cur1, fn, g.d_crc, 1u << b1);
+}
+
+template <int LEVEL, bool PEER>
+static void launch_scatter_l(int pmode, const uint2* in, uint2* out, const unsigned long long* n_ptr, uint64_t n,
+                             const uint32_t* off, const uint32_t* tiles, uint32_t* cursor, const PartFn& pf, uint32_t nbins,
+                             uint32_t P1L, const PeerBufs& peers, const uint32_t* abort_flag) {
+    const int grid = g.sms * g.occ_scatter;
+    switch (pmode) {
+        case 0:
+            k_scatter<LEVEL, 0, PEER><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, out, n_ptr, n, off, tiles, cursor, pf,
+                                                                                        g.d_crc, nbins, P1L, peers, abort_flag);
+            break;
+        case 1:
+            k_scatter<LEVEL, 1, PEER><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, out, n_ptr, n, off, tiles, cursor, pf,
+                                                                                        g.d_crc, nbins, P1L, peers, abort_flag);
+            break;
+        default:
+            k_scatter<LEVEL, 2, PEER><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, out, n_ptr, n, off, tiles, cursor, pf,
+                                                                                        g.d_crc, nbins, P1L, peers, abort_flag);
+            break;
+    }
+}
+
+static void launch_barrier(const Fab& f, Control* ctrl) {
+    // 2 s at the SM clock: a peer that never arrives ends the wait instead of hanging the GPU
+    k_barrier<<<1, 32, 0, g.stream>>>(f.flags, (uint32_t)f.world, (uint32_t)f.rank, f.epoch, &ctrl->err,
+                                      2ll * g.clock_khz * 1000ll);
+}
+
+// histogram rows of all ranks -> offsets; scatter level 1 (into the owners' buffers) and level 2 (local).
+// Returns the final partitions of this rank. `hist` is this rank's row (already computed); `rows` where every rank's row
+// is gathered (world > 1), `recv` the level-1 destination of every owner, `t2` the local level-2 output.
+static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, const uint2* in, uint64_t n,
+                                  const unsigned long long* n_ptr, uint32_t* hist, const PeerPtrs& rows,
+                                  const PeerBufs& recv, uint64_t capacity, uint32_t* off, uint2* t2,
+                                  unsigned long long* n_own, Control* ctrl, int& launches) {
+    const uint32_t P = 1u << pf.bits;
+    const uint32_t b1 = pf.bits - pf.b2;
+    const uint32_t* hist_all = hist;
+    if (f.world > 1) {
+        k_push_rows<<<dim3(4, f.world), 256, 0, g.stream>>>(rows, (uint32_t)f.world, (uint32_t)f.rank, hist, P);
+        launch_barrier(f, ctrl);
+        hist_all = reinterpret_cast<const uint32_t*>(rows.p[f.rank]);
+        launches += 2;
+    }
+    k_scan_dist<<<1, 1024, 0, g.stream>>>(hist_all, (uint32_t)f.world, (uint32_t)f.rank, P, pf.b2, capacity, off,
+                                          g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(), g.tiles.as<uint32_t>(), n_own,
+                                          &ctrl->abort);
     launches++;
-    if (b2 == 0) return t1;
-    k_scatter<2><<<g.sms * g.occ_scatter2, kScatterThreads, kScatterSmem, stream>>>(t1, t2, nullptr, n, off, tiles, cur2,
-                                                                                   fn, g.d_crc, 1u << b2);
+    uint2* t1 = recv.buf[f.rank];
+    if (f.world > 1) {
+        launch_scatter_l<1, true>(pmode, in, t1, n_ptr, n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pf, 1u << b1, 0u,
+                                  recv, &ctrl->abort);
+        launch_barrier(f, ctrl);  // every rank's tuples have arrived
+        launches += 2;
+    } else {
+        launch_scatter_l<1, false>(pmode, in, t1, n_ptr, n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pf, 1u << b1, 0u,
+                                   recv, nullptr);
+        launches++;
+    }
+    if (pf.b2 == 0) return t1;
+    launch_scatter_l<2, false>(pmode, t1, t2, nullptr, capacity, off, g.tiles.as<uint32_t>(), g.cur2.as<uint32_t>(), pf,
+                               1u << pf.b2, (1u << b1) / (uint32_t)f.world, recv, f.world > 1 ? &ctrl->abort : nullptr);
     launches++;
     return t2;
 }
 
-static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t* args) {
+static void ensure_workspace(uint64_t capR, uint64_t nS, uint64_t capS, const bloom_filter_args_t* args, bool dist) {
     const size_t P = 1u << kMaxRadixBits;
-    if (args) g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
+    if (args && !dist) g.filter.ensure(std::max<uint64_t>(args->m / 8, 16));
     g.histR.ensure(P * 4);
     g.histS.ensure(P * 4);
     g.offR.ensure((P + 1) * 4);
@@ -407,29 +428,48 @@ static void ensure_workspace(uint64_t nR, uint64_t nS, const bloom_filter_args_t
     g.cur1.ensure(((size_t)1 << kMaxLevelBits) * 4);
     g.cur2.ensure(P * 4);
     g.tiles.ensure((((size_t)1 << kMaxLevelBits) + 1) * 4);
-    g.cur1b.ensure(((size_t)1 << kMaxLevelBits) * 4);
-    g.cur2b.ensure(P * 4);
-    g.tilesb.ensure((((size_t)1 << kMaxLevelBits) + 1) * 4);
     g.work.ensure((P + 1) * 4);
-    g.work_part.ensure((P + nS / kSChunk + 2) * 4);  // one entry per join work item
+    g.work_part.ensure((P + capS / kSChunk + 2) * 4);  // one entry per join work item
     g.ctrl.ensure(sizeof(Control));
-    g.rt1.ensure(std::max<uint64_t>(nR, 1) * 8);
-    g.rp.ensure(std::max<uint64_t>(nR, 1) * 8);
-    g.sc.ensure(std::max<uint64_t>(nS, 1) * 8);
-    g.st1.ensure(std::max<uint64_t>(nS, 1) * 8);
+    if (!dist) g.rt1.ensure(std::max<uint64_t>(capR, 1) * 8 + 64);
+    g.rp.ensure(std::max<uint64_t>(capR, 1) * 8 + 64);
+    g.sc.ensure(std::max<uint64_t>(nS, 1) * 8 + 64);
+    if (!dist) g.st1.ensure(std::max<uint64_t>(nS, 1) * 8 + 64);
+    else g.s2.ensure(std::max<uint64_t>(capS, 1) * 8 + 64);
 }
 
-// The join on device-resident relations. args == nullptr: plain radix join.
-// copies the result words of a join out of the control block (async / graph-captured joins)
-__global__ void k_export_results(const Control* c, unsigned long long* out) {
+// how the join partitions: 0 radix bits of the key (the reference's clustering), 1 / 2 the filter-slice index of a
+// BASIC (k <= 1) / BLOCKED filter, which lets K1' build the filter in shared memory and -- across GPUs -- makes every rank
+// the builder of exactly its slice of the replicated filter
+static int pick_mode(const bloom_filter_args_t* a, int bits, int world) {
+    if (!a || !g.hash_partition || bits < 1) return 0;
+    const bool basic = a->variant == BASIC;
+    if (basic && a->k > 1) return 0;  // a key's bits spread over the whole filter: not sliceable
+    const uint64_t units = basic ? a->m : a->m / a->B;  // what is sliced: bits, or whole blocks
+    if (ilog2_u64(units) < bits) return 0;
+    const uint64_t slice_bits = a->m >> bits;
+    if (slice_bits < 32 || slice_bits / 8 > (uint64_t)kFilterSliceSmemMax) return 0;
+    // one GPU: for small filters the plain global atomics are as fast (C0: 1.71 vs 1.80 ms) and the radix table index has
+    // shorter chains, so the slice build is used for filters beyond L2-friendly sizes unless forced
+    if (world == 1 && g.hash_partition == 1 && a->m / 8 <= (32ull << 20)) return 0;
+    return basic ? 1 : 2;
+}
+
+__global__ void k_export_row(Control* c, int has_filter) {
     if (threadIdx.x == 0) {
-        out[0] = c->acc.matches;
-        out[1] = c->acc.cpair;
-        out[2] = c->acc.crpay;
-        out[3] = c->acc.cspay;
-        out[4] = c->acc.ckey;
-        out[5] = c->survivors;
+        c->row[0] = c->acc.matches;
+        c->row[1] = c->acc.cpair;
+        c->row[2] = c->acc.crpay;
+        c->row[3] = c->acc.cspay;
+        c->row[4] = c->acc.ckey;
+        c->row[5] = has_filter ? c->survivors : 0ull;
+        c->row[6] = (unsigned long long)c->abort | ((unsigned long long)c->err << 8);
+        c->row[7] = 0ull;
+        for (int i = 0; i < 8; i++) c->out[i] = c->row[i];  // one GPU: the sum is the row itself
     }
+}
+__global__ void k_copy8(const unsigned long long* src, unsigned long long* dst) {
+    if (threadIdx.x < 8) dst[threadIdx.x] = src[threadIdx.x];
 }
 
 // S arriving from the host in chunks: chunk c (chunk_tuples tuples, the last one shorter) is complete when ev[c] fires
@@ -439,202 +479,226 @@ struct SFeed {
     cudaEvent_t* ev;
 };
 
-static void run_join(const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS, const bloom_filter_args_t* args,
-                     hwbrj_stats_t& st, const unsigned long long* nR_dev = nullptr, uint64_t nR_expect = 0,
-                     const unsigned long long* nS_dev = nullptr, const SFeed* feed = nullptr,
-                     unsigned long long* d_async_out = nullptr) {
-    // d_async_out != nullptr: enqueue only (no events, no host synchronisation -- capturable in a CUDA graph); the six
-    // result words {matches, cpair, crpay, cspay, ckey, survivors} are left in d_async_out (device)
-    const bool async_mode = d_async_out != nullptr;
-    auto rec = [&](cudaEvent_t e, cudaStream_t s) {
-        if (!async_mode) CK(cudaEventRecord(e, s));
+// The join of this rank's chunks dR / dS (one GPU: the whole relations). args == nullptr: plain radix join.
+// f describes the participating GPUs (f.world == 1: the plain workspace). r_total = |R| over all ranks (sizes the fan-out).
+// Modes: kSync enqueues, waits and fills st; kEnqueue records the timing events but does not wait (collect_join() does:
+// one host thread drives several GPUs); kCapture records no events and leaves the eight result words {matches, cpair,
+// crpay, cspay, ckey, filtered, flags, 0}, summed over the ranks, in d_async_out (capturable in a CUDA graph).
+// Returns 0, or -2 when a receive buffer was too small / a peer timed out (results invalid).
+enum JoinMode { kSync, kEnqueue, kCapture };
+static int collect_join(hwbrj_stats_t& st, bool has_filter);
+
+static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS, uint64_t nS,
+                    const bloom_filter_args_t* args, uint64_t r_total, hwbrj_stats_t& st, const SFeed* feed = nullptr,
+                    JoinMode mode = kSync, unsigned long long* d_async_out = nullptr) {
+    const bool dist = f.world > 1;
+    auto rec = [&](int e) {
+        if (mode != kCapture) CK(cudaEventRecord(g.ev[e], g.stream));
     };
-    // nR/nS are exact counts, or capacities when the real counts live on the device (nR_dev/nS_dev)
     // 32-bit tuple indices; the slack keeps "index + one batch of loads" from wrapping in the kernels
-    if (nR >= (1ull << 32) - (1ull << 20) || nS >= (1ull << 32) - (1ull << 20))
-        die("relations of 2^32 - 2^20 or more tuples are not supported");
+    if (nR >= (1ull << 32) - (1ull << 20) || nS >= (1ull << 32) - (1ull << 20) || f.cap_r >= (1ull << 32) - (1ull << 20) ||
+        f.cap_s >= (1ull << 32) - (1ull << 20))
+        die("relations of 2^32 - 2^20 or more tuples per GPU are not supported");
     if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
-    if (args && nS_dev) die("device-side S count is only supported for the filter-less join");
-    ensure_workspace(nR, nS, args);
-    // the R side may have been partitioned already (hwbrj_join_prepare_r, filter-less joins of exactly this relation)
-    const bool prepared = !args && g.prep.valid && g.prep.d == dR && g.prep.n == nR && g.prep.n_dev == nR_dev;
-    g.prep.valid = false;  // one use; a stale preparation of another relation is simply dropped
-    const int bits = prepared ? g.prep.bits : pick_bits(nR_dev ? nR_expect : nR);
-    const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
-    const uint32_t P = 1u << bits;
-    const uint32_t pmask = P - 1u;
+    if (args && dist && args->m / 8 > f.filter_bytes) die("the filter exceeds the size the GPU group was created for");
+    ensure_workspace(dist ? f.cap_r : nR, nS, dist ? f.cap_s : nS, args, dist);
+    const int bits = pick_bits(r_total, f.gbits);
+    const int b2 = pick_b2(bits, f.gbits);
+    const int pmode = pick_mode(args, bits, f.world);
+    const uint32_t P = 1u << bits, PL = P / (uint32_t)f.world;
     int launches = 0;
     Control* ctrl = g.ctrl.as<Control>();
+    PartFn pf;
+    memset(&pf, 0, sizeof(pf));
+    pf.bits = (uint32_t)bits;
+    pf.b2 = (uint32_t)b2;
+    pf.seed = 42u;
+    if (pmode == 1) {
+        pf.size_mask = (uint32_t)(args->m - 1);
+        pf.hshift = (uint32_t)(ilog2_u64(args->m) - bits);
+    } else if (pmode == 2) {
+        pf.size_mask = (uint32_t)(args->m / args->B - 1);
+        pf.hshift = (uint32_t)(ilog2_u64(args->m / args->B) - bits);
+    }
+    // level-1 receive buffers and filters: the symmetric memory of the GPU group, or the plain workspace
+    PeerBufs recvR = f.recvR, recvS = f.recvS;
+    PeerPtrs filt = f.filter;
+    uint32_t* my_filter = nullptr;
+    if (!dist) {
+        recvR.buf[0] = g.rt1.as<uint2>();
+        recvS.buf[0] = g.st1.as<uint2>();
+        filt.p[0] = g.filter.p;
+    }
+    recvR.shift = recvS.shift = (uint32_t)(bits - b2 - f.gbits);
+    if (args) my_filter = reinterpret_cast<uint32_t*>(filt.p[f.rank]);
+    // non-sliceable filter on several GPUs: every rank inserts its R chunk into a full-size partial, then OR-combine
+    uint32_t* insert_filter = (args && pmode == 0 && dist) ? reinterpret_cast<uint32_t*>(f.partial.p[f.rank]) : my_filter;
 
     // ---- untimed set-up (the reference allocates and zeroes its filter before the timed region, :1583) ----
-    rec(g.ev[0], g.stream);
-    if (args) CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
-    if (!prepared) CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));  // else: in use on the side stream
+    rec(0);
+    if (args && pmode == 0) CK(cudaMemsetAsync(insert_filter, 0, std::max<uint64_t>(args->m / 8, 16), g.stream));
+    CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
     CK(cudaMemsetAsync(g.histS.p, 0, P * 4, g.stream));
     CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
 
     // ---- timed region ----------------------------------------------------------------------------------------
-    rec(g.ev[1], g.stream);
+    rec(1);
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
     int nranges = 1;
-    const int hist_smem = (int)((P + kCrcSmemWords) * 4);
-    const int grid_hist = g.sms * 2;
-    // Hash-partitioned variant (BASIC, k <= 1): the join partitions on the filter-slice index, so each partition owns a
-    // contiguous m/P-bit slice of the filter and K1' builds it in shared memory -- no global atomics, R read once less.
-    PartFn pf;
-    // Used when the filter is too big for its atomics to stay L2-resident (> 32 MiB: K1 1.25 -> 0.68 ms at C1); for
-    // small filters the plain atomics are faster (C0: 1.71 vs 1.80 ms) and the radix table index has shorter chains.
-    if (args && g.hash_partition && args->variant == BASIC && args->k <= 1 && bits >= 1 &&
-        (args->m / 8 > (32ull << 20) || g.hash_partition_force) && ilog2_u64(args->m) >= bits + 5 &&
-        (args->m >> bits) / 8 <= 96 * 1024 && !g.overlap_r_partition) {
-        pf.hash = true;
-        pf.size_mask = (uint32_t)(args->m - 1);
-        pf.log2m = ilog2_u64(args->m);
-    }
-    const uint32_t hshift = pf.hash ? (uint32_t)(pf.log2m - bits) : 0u;
     if (args) {
-        bp = make_bloom(args, 42u, g.filter.as<uint32_t>());  // seed 42: parallel_radix_join_bloom.c:1583,1823
+        bp = make_bloom(args, 42u, insert_filter);  // seed 42: parallel_radix_join_bloom.c:1583,1823
         nranges = pick_ranges(args);
-        bp.nranges = (uint32_t)nranges;
-        bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-        if (pf.hash) {
-            k_build_hist<false, true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc,
-                                                                               g.histR.as<uint32_t>(), pmask, hshift);
+        set_ranges(bp, args, nranges);
+    }
+    // K1: partition histogram of this rank's R chunk; the radix variant inserts into the filter on the way
+    if (args && pmode == 0) {
+        const int smem = (int)((P + kCrcSmemWords) * 4);
+        for (int r = 0; r < nranges; r++) {
+            bp.range_id = (uint32_t)r;
+            k_build_hist<true, 0><<<g.sms * 2, 1024, smem, g.stream>>>(dR, nR, nullptr, bp, g.d_crc, g.histR.as<uint32_t>(), pf);
             launches++;
-        } else {
-            for (int r = 0; r < nranges; r++) {
-                bp.range_id = (uint32_t)r;
-                k_build_hist<true><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
-                launches++;
-            }
         }
-    } else if (!prepared) {
-        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(dR, nR, nR_dev, bp, g.d_crc, g.histR.as<uint32_t>(), pmask);
-        launches++;
-    }
-    rec(g.ev[2], g.stream);
-    // R partitioning (HBM-bound) runs on a side stream underneath the S probe (L1TEX/issue-bound) when a filter is used
-    const bool overlap = g.overlap_r_partition && args != nullptr;
-    const uint2* Rp;
-    if (prepared) {
-        Rp = g.prep.Rp;  // partitioned on the side stream; joined below, before the work list
-        launches += g.prep.launches;
-    } else if (overlap) {
-        CK(cudaStreamWaitEvent(g.side_stream, g.ev[2], 0));
-        rec(g.ev_side[0], g.side_stream);
-        Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(), g.rt1.as<uint2>(),
-                           g.rp.as<uint2>(), launches, g.side_stream, true);
-        rec(g.ev_side[1], g.side_stream);
     } else {
-        Rp = run_partition(dR, nR, nR_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(), g.rt1.as<uint2>(),
-                           g.rp.as<uint2>(), launches, nullptr, false, pf);
-    }
-    rec(g.ev_side[2], g.stream);
-    if (pf.hash && args->k >= 1) {  // K1': the filter, slice by slice, from the partitioned R (k = 0 sets no bit)
-        const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
-        k_filter_from_parts<<<g.sms * 4, 512, 2 * slice_words * 4, g.stream>>>(Rp, g.offR.as<uint32_t>(), P, g.filter.as<uint32_t>(),
-                                                                          slice_words, 42u, pf.size_mask);
+        launch_hist(pmode, dR, nR, nullptr, bp, g.histR.as<uint32_t>(), pf);
         launches++;
     }
-    rec(g.ev[3], g.stream);
-    const uint2* Sin = dS;
-    const unsigned long long* n_dev = nS_dev;
+    rec(2);
+    const uint2* Rp = run_partition(f, pmode, pf, dR, nR, nullptr, g.histR.as<uint32_t>(), f.histR, recvR,
+                                    dist ? f.cap_r : nR, g.offR.as<uint32_t>(), g.rp.as<uint2>(), &ctrl->n_own_r, ctrl,
+                                    launches);
+    rec(3);
     if (args) {
-        if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(nS, 1) * 8);
+        bp.filter = my_filter;
+        if (pmode != 0) {  // K1': the filter, slice by slice, from the partitioned R; every word is written
+            const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
+            const uint32_t nbuf = 2u * slice_words * 4u <= 96u * 1024u ? 2u : 1u;
+            const int smem = (int)(nbuf * slice_words * 4u);
+            const int grid = g.sms * (smem <= 48 * 1024 ? 4 : 1);
+            const uint32_t gbase = (uint32_t)f.rank * PL;
+#define HWBRJ_K1P(BL, PE)                                                                                           \
+    k_filter_from_parts<BL, PE><<<grid, 512, smem, g.stream>>>(Rp, g.offR.as<uint32_t>(), PL, gbase, slice_words, bp, \
+                                                               g.d_crc, filt, (uint32_t)f.world, nbuf)
+            if (pmode == 2) {
+                if (dist) HWBRJ_K1P(true, true); else HWBRJ_K1P(true, false);
+            } else {
+                if (dist) HWBRJ_K1P(false, true); else HWBRJ_K1P(false, false);
+            }
+#undef HWBRJ_K1P
+            launches++;
+        } else if (dist) {  // partial filters are complete on every rank (the barrier after the level-1 scatter)
+            const uint64_t n16 = std::max<uint64_t>(args->m / 8, 16) / 16;
+            const uint64_t per = n16 / (uint64_t)f.world;
+            k_filter_or_bcast<<<g.sms * 4, 256, 0, g.stream>>>(f.partial, f.filter, (uint32_t)f.world, per * f.rank,
+                                                               f.rank == f.world - 1 ? n16 - per * f.rank : per);
+            launches++;
+        }
+        if (dist) {
+            launch_barrier(f, ctrl);  // the replicated filter is complete on every rank
+            launches++;
+        }
+    }
+    rec(4);
+    const uint2* Sin = dS;
+    const unsigned long long* n_dev = nullptr;
+    if (args) {
         if (feed) {  // probe every chunk as soon as its host->device copy has completed
             for (int c = 0; c < feed->nchunks; c++) {
                 const uint64_t off = (uint64_t)c * feed->chunk_tuples;
                 const uint64_t cnt = std::min<uint64_t>(feed->chunk_tuples, nS - off);
                 CK(cudaStreamWaitEvent(g.stream, feed->ev[c], 0));
-                launches += run_probe(dS + off, cnt, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
-                                      nranges > 2 ? g.d1.as<uint2>() : nullptr);
+                launches += run_probe(dS + off, cnt, nullptr, bp, nranges, g.sc.as<uint2>(), &ctrl->survivors);
             }
         } else {
-            launches += run_probe(dS, nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
-                                  nranges > 2 ? g.d1.as<uint2>() : nullptr);
+            launches += run_probe(dS, nS, nullptr, bp, nranges, g.sc.as<uint2>(), &ctrl->survivors);
         }
         Sin = g.sc.as<uint2>();
         n_dev = &ctrl->survivors;
     }
-    rec(g.ev[4], g.stream);  // ms_probe = the K2 launches only
-    // radix histogram of the tuples that go on to the join (survivors, or all of S without a filter)
-    if (pf.hash)
-        k_build_hist<false, true><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc,
-                                                                           g.histS.as<uint32_t>(), pmask, hshift);
-    else
-        k_build_hist<false><<<grid_hist, 1024, hist_smem, g.stream>>>(Sin, nS, n_dev, bp, g.d_crc, g.histS.as<uint32_t>(), pmask);
+    rec(5);  // ms_probe = the K2 launches only
+    // partition histogram of the tuples that go on to the join (survivors, or all of S without a filter)
+    launch_hist(pmode, Sin, nS, n_dev, bp, g.histS.as<uint32_t>(), pf);
     launches++;
-    // with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc
-    const uint2* Sp = run_partition(Sin, nS, n_dev, bits, b2, g.histS.as<uint32_t>(), g.offS.as<uint32_t>(),
-                                    g.st1.as<uint2>(), g.sc.as<uint2>(), launches, nullptr, false, pf);
-    rec(g.ev[5], g.stream);
-    if (overlap) CK(cudaStreamWaitEvent(g.stream, g.ev_side[1], 0));
-    if (prepared) CK(cudaStreamWaitEvent(g.stream, g.ev_prep_done, 0));
-    k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), P, g.work.as<uint32_t>(),
+    // one GPU with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc ; several GPUs: -> owner's recvS -> s2
+    const uint2* Sp = run_partition(f, pmode, pf, Sin, nS, n_dev, g.histS.as<uint32_t>(), f.histS, recvS, dist ? f.cap_s : nS,
+                                    g.offS.as<uint32_t>(), dist ? g.s2.as<uint2>() : g.sc.as<uint2>(), &ctrl->n_own_s, ctrl,
+                                    launches);
+    rec(6);
+    k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), PL, g.work.as<uint32_t>(),
                                          g.work_part.as<uint32_t>());
     launches++;
-    if (pf.hash)
+    if (pmode != 0)
         k_join<true><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
-            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), P, (uint32_t)bits,
-            &ctrl->item_counter, &ctrl->acc);
+            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), PL,
+            (uint32_t)bits, &ctrl->item_counter, &ctrl->acc);
     else
         k_join<false><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
-            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), P, (uint32_t)bits,
-            &ctrl->item_counter, &ctrl->acc);
+            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), PL,
+            (uint32_t)bits, &ctrl->item_counter, &ctrl->acc);
     launches++;
     g.last_Rp = Rp;
     g.last_Sp = Sp;
-    g.last_P = P;
+    g.last_P = PL;
     g.last_bits = (uint32_t)bits;
-    g.last_hash = pf.hash;
-    rec(g.ev[6], g.stream);
-    if (async_mode) {
-        k_export_results<<<1, 32, 0, g.stream>>>(ctrl, d_async_out);
-        st.kernel_launches = launches + 1;
-        st.radix_bits = bits;
-        st.range_passes = nranges;
-        return;
+    g.last_hash = pmode != 0;
+    rec(7);
+    // the result words; several GPUs: all-gather of the rows over NVLink, barrier, local sum
+    k_export_row<<<1, 32, 0, g.stream>>>(ctrl, args ? 1 : 0);
+    launches++;
+    if (dist) {
+        k_push_rows<<<dim3(1, f.world), 32, 0, g.stream>>>(f.rows, (uint32_t)f.world, (uint32_t)f.rank,
+                                                           reinterpret_cast<const uint32_t*>(ctrl->row), 16u);
+        launch_barrier(f, ctrl);  // also: every rank has finished reading its receive buffers -> the next join may start
+        k_reduce_rows<<<1, 32, 0, g.stream>>>(reinterpret_cast<const unsigned long long*>(f.rows.p[f.rank]), (uint32_t)f.world,
+                                              ctrl->out);
+        launches += 3;
     }
+    rec(8);
+    st.kernel_launches = launches;
+    st.radix_bits = bits;
+    st.range_passes = nranges;
+    st.n_gpus = f.world;
+    if (mode == kCapture) {
+        k_copy8<<<1, 32, 0, g.stream>>>(ctrl->out, d_async_out);
+        st.kernel_launches++;
+        return 0;
+    }
+    if (mode == kEnqueue) return 0;
+    return collect_join(st, args != nullptr);
+}
+
+// waits for the join enqueued on this device's stream and fills the result and timing fields of st
+static int collect_join(hwbrj_stats_t& st, bool has_filter) {
     Control h;
-    CK(cudaMemcpyAsync(&h, ctrl, sizeof(Control), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(&h, g.ctrl.p, sizeof(Control), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaGetLastError());
-
     auto ms = [&](int a, int b) {
         float v = 0;
         CK(cudaEventElapsedTime(&v, g.ev[a], g.ev[b]));
         return v;
     };
-    st.matches = (int64_t)h.acc.matches;
-    st.filtered = args ? (int64_t)h.survivors : -1;
-    st.checksum_pair = h.acc.cpair;
-    st.checksum_rpay = h.acc.crpay;
-    st.checksum_spay = h.acc.cspay;
-    st.checksum_key = h.acc.ckey;
+    st.matches = (int64_t)h.out[0];
+    st.checksum_pair = h.out[1];
+    st.checksum_rpay = h.out[2];
+    st.checksum_spay = h.out[3];
+    st.checksum_key = h.out[4];
+    st.filtered = has_filter ? (int64_t)h.out[5] : -1;
     st.ms_memset = ms(0, 1);
-    st.ms_total = ms(1, 6);
-    st.ms_build = ms(1, 2);
+    st.ms_total = ms(1, 8);
+    st.ms_build = ms(1, 2) + ms(3, 4);  // histogram (+ insert), and the slice build / filter exchange after the scatter
     st.ms_part_r = ms(2, 3);
-    if (pf.hash) {  // the filter is built after the scatter passes: book it under "build"
-        float f = 0;
-        CK(cudaEventElapsedTime(&f, g.ev_side[2], g.ev[3]));
-        st.ms_build += f;
-        st.ms_part_r -= f;
-    }
-    if (overlap) CK(cudaEventElapsedTime(&st.ms_part_r, g.ev_side[0], g.ev_side[1]));  // overlapped with ms_probe
-    st.ms_probe = ms(3, 4);
-    st.ms_part_s = ms(4, 5);
-    st.ms_join = ms(5, 6);
-    st.kernel_launches = launches;
-    st.radix_bits = bits;
-    st.range_passes = nranges;
-    st.n_gpus = 1;
+    st.ms_probe = ms(4, 5);
+    st.ms_part_s = ms(5, 6);
+    st.ms_join = ms(6, 8);
+    st.owned_r = h.n_own_r;
+    st.owned_s = h.n_own_s;
     st.d2h_bytes += sizeof(Control);
+    return h.out[6] ? -2 : 0;
 }
 
 static void print_reference_lines(const hwbrj_stats_t& st, uint64_t nS, bool bloom_line) {
-    if (g.quiet) return;
+    if (g_quiet) return;
     // stdout contract of parallel_radix_join_bloom.c:1253 and print_timing (:1510-1547)
     if (bloom_line) fprintf(stdout, "S-tuples after filter: %d\n", (int)st.filtered);
     const double total_us = st.ms_total * 1000.0;
@@ -662,19 +726,275 @@ static void h2d(void* dst, const void* src, size_t bytes) {
     if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
 }
 
-// host-buffer entry: copy in, join, fill result_t (join_init_run, :1561-1778)
+static Fab single_fab() {
+    Fab f;
+    memset(&f, 0, sizeof(f));
+    f.world = 1;
+    return f;
+}
+
+}  // namespace hwbrj
+
+// ---- a group of GPUs that join together ----------------------------------------------------------------
+// Every rank allocates one "symmetric" block (same layout on every rank) that its peers map: barrier flags, the gathered
+// histogram and result rows, the replicated filter (+ a partial filter for non-sliceable filters) and the two receive
+// buffers of the level-1 routing. Ranks of other processes are mapped through CUDA IPC, ranks of this process through
+// peer access.
+struct hwbrj_dist {
+    int rank = 0, world = 1, dev = 0;
+    unsigned char* base = nullptr;
+    size_t bytes = 0;
+    size_t off_epoch = 0, off_histR = 0, off_histS = 0, off_rows = 0, off_filter = 0, off_partial = 0, off_recvR = 0, off_recvS = 0;
+    uint64_t cap_r = 0, cap_s = 0, filter_bytes = 0;
+    unsigned char* peer[hwbrj::kMaxPeers] = {nullptr};
+    bool ipc_opened[hwbrj::kMaxPeers] = {false};
+    bool connected = false;
+    hwbrj::Fab fab;
+    void* d_out8 = nullptr;  // result words of an enqueued join
+};
+
+namespace hwbrj {
+
+struct DistHandle {  // what travels between the ranks (HWBRJ_DIST_HANDLE_BYTES)
+    cudaIpcMemHandle_t ipc;
+    int32_t pid, dev;
+    uint64_t ptr, bytes, cap_r, cap_s, filter_bytes;
+    unsigned char pad[HWBRJ_DIST_HANDLE_BYTES - 64 - 8 - 40];
+};
+static_assert(sizeof(DistHandle) == HWBRJ_DIST_HANDLE_BYTES, "handle size");
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static hwbrj_dist* dist_create(int rank, int world, uint64_t cap_r, uint64_t cap_s, uint64_t filter_bytes, void* handle_out) {
+    if (world < 1 || world > kMaxPeers || (world & (world - 1)) || rank < 0 || rank >= world) return nullptr;
+    hwbrj_dist* d = new hwbrj_dist;
+    d->rank = rank;
+    d->world = world;
+    d->dev = g.dev;
+    d->cap_r = cap_r;
+    d->cap_s = cap_s;
+    d->filter_bytes = align_up(std::max<uint64_t>(filter_bytes, 16), 256);
+    const size_t P = (size_t)1 << kMaxRadixBits;
+    size_t off = kMaxPeers * kFlagStride * 4;  // flags first
+    d->off_epoch = off; off += 256;
+    d->off_histR = off; off += (size_t)world * P * 4;
+    d->off_histS = off; off += (size_t)world * P * 4;
+    d->off_rows = off; off += align_up((size_t)world * 64, 256);
+    d->off_filter = off; off += d->filter_bytes;
+    d->off_partial = off; off += d->filter_bytes;
+    d->off_recvR = off; off += align_up(cap_r * 8 + 64, 256);
+    d->off_recvS = off; off += align_up(cap_s * 8 + 64, 256);
+    d->bytes = off;
+    cudaError_t e = cudaMalloc(&d->base, d->bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete d;
+        return nullptr;
+    }
+    CK(cudaMemset(d->base, 0, d->off_filter));  // flags, epoch, rows
+    CK(cudaMalloc(&d->d_out8, 64));
+    DistHandle h;
+    memset(&h, 0, sizeof(h));
+    if (cudaIpcGetMemHandle(&h.ipc, d->base) != cudaSuccess) cudaGetLastError();  // same-process peers do not need it
+    h.pid = (int32_t)getpid();
+    h.dev = d->dev;
+    h.ptr = (uint64_t)(uintptr_t)d->base;
+    h.bytes = d->bytes;
+    h.cap_r = cap_r;
+    h.cap_s = cap_s;
+    h.filter_bytes = d->filter_bytes;
+    if (handle_out) memcpy(handle_out, &h, sizeof(h));
+    return d;
+}
+
+static int dist_connect(hwbrj_dist* d, const void* all_handles) {
+    const DistHandle* hs = reinterpret_cast<const DistHandle*>(all_handles);
+    for (int r = 0; r < d->world; r++) {
+        const DistHandle& h = hs[r];
+        if (h.bytes != d->bytes || h.cap_r != d->cap_r || h.cap_s != d->cap_s || h.filter_bytes != d->filter_bytes) return -3;
+        if (r == d->rank) {
+            d->peer[r] = d->base;
+        } else if (h.pid == (int32_t)getpid()) {  // a device of this process: peer access
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, d->dev, h.dev));
+            if (!can) return -4;
+            cudaError_t e = cudaDeviceEnablePeerAccess(h.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return -4;
+            cudaGetLastError();
+            d->peer[r] = reinterpret_cast<unsigned char*>((uintptr_t)h.ptr);
+        } else {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                return -5;
+            }
+            d->peer[r] = reinterpret_cast<unsigned char*>(p);
+            d->ipc_opened[r] = true;
+        }
+    }
+    Fab& f = d->fab;
+    memset(&f, 0, sizeof(f));
+    f.world = d->world;
+    f.rank = d->rank;
+    f.gbits = ilog2_u64((uint64_t)d->world);
+    for (int r = 0; r < d->world; r++) {
+        f.flags.p[r] = d->peer[r];
+        f.histR.p[r] = d->peer[r] + d->off_histR;
+        f.histS.p[r] = d->peer[r] + d->off_histS;
+        f.rows.p[r] = d->peer[r] + d->off_rows;
+        f.filter.p[r] = d->peer[r] + d->off_filter;
+        f.partial.p[r] = d->peer[r] + d->off_partial;
+        f.recvR.buf[r] = reinterpret_cast<uint2*>(d->peer[r] + d->off_recvR);
+        f.recvS.buf[r] = reinterpret_cast<uint2*>(d->peer[r] + d->off_recvS);
+    }
+    f.epoch = reinterpret_cast<uint32_t*>(d->base + d->off_epoch);
+    f.cap_r = d->cap_r;
+    f.cap_s = d->cap_s;
+    f.filter_bytes = d->filter_bytes;
+    d->connected = true;
+    return 0;
+}
+
+static void dist_destroy(hwbrj_dist* d) {
+    if (!d) return;
+    invalidate_last();
+    for (int r = 0; r < d->world; r++)
+        if (d->ipc_opened[r]) cudaIpcCloseMemHandle(d->peer[r]);
+    if (d->base) cudaFree(d->base);
+    if (d->d_out8) cudaFree(d->d_out8);
+    cudaGetLastError();
+    delete d;
+}
+
+// ---- host-buffer entry: copy in, join, fill result_t (join_init_run, :1561-1778) ---------------------------------------
+static std::vector<hwbrj_dist*> g_group;  // the GPUs of this process that join together (hwbrj_set_gpus)
+
+static void group_release() {
+    for (size_t i = 0; i < g_group.size(); i++) {
+        CK(cudaSetDevice((int)i));
+        init_ctx();
+        CK(cudaDeviceSynchronize());
+        dist_destroy(g_group[i]);
+    }
+    g_group.clear();
+}
+
+// (re)creates the in-process GPU group when it is missing or too small
+static void group_ensure(int n, uint64_t cap_r, uint64_t cap_s, uint64_t filter_bytes) {
+    if ((int)g_group.size() == n && g_group[0]->cap_r >= cap_r && g_group[0]->cap_s >= cap_s &&
+        g_group[0]->filter_bytes >= filter_bytes)
+        return;
+    int home = 0;
+    CK(cudaGetDevice(&home));
+    group_release();
+    std::vector<DistHandle> hs(n);
+    for (int i = 0; i < n; i++) {
+        CK(cudaSetDevice(i));
+        init_ctx();
+        hwbrj_dist* d = dist_create(i, n, cap_r, cap_s, filter_bytes, &hs[i]);
+        if (!d) die("cannot allocate the receive buffers of GPU %d (%llu + %llu tuples)", i, (unsigned long long)cap_r,
+                    (unsigned long long)cap_s);
+        g_group.push_back(d);
+    }
+    for (int i = 0; i < n; i++) {
+        CK(cudaSetDevice(i));
+        init_ctx();
+        int rc = dist_connect(g_group[i], hs.data());
+        if (rc) die("GPU %d cannot map its peers (rc %d): the GPUs of a join need peer access (NVLink)", i, rc);
+    }
+    CK(cudaSetDevice(home));
+    init_ctx();
+}
+
+// contiguous chunk of rank i (the reference's per-thread chunks, :1646-1672: the last one takes the remainder); chunk
+// starts are kept even so that every chunk stays 16-byte aligned
+static void chunk_of(uint64_t n, int world, int i, uint64_t& begin, uint64_t& count) {
+    const uint64_t per = (n / (uint64_t)world) & ~1ull;
+    begin = per * (uint64_t)i;
+    count = i == world - 1 ? n - begin : per;
+}
+
+static result_t* host_join_multi(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args,
+                                 bool print_filtered) {
+    auto t0 = std::chrono::steady_clock::now();
+    const int G = g_gpus;
+    const uint64_t nR = relR->num_tuples, nS = relS->num_tuples;
+    int home = 0;
+    CK(cudaGetDevice(&home));
+    // receive capacities: R keys are spread by a hash of the key (25 % slack), S worst case = everything survives and
+    // lands on one owner (a hot key)
+    group_ensure(G, nR / G + nR / (4 * G) + (1u << 16), nS + 2, args ? args->m / 8 : 16);
+    std::vector<hwbrj_stats_t> sts(G);
+    for (int i = 0; i < G; i++) {  // first all copies (a pageable source makes them block the host) ...
+        CK(cudaSetDevice(i));
+        init_ctx();
+        memset(&sts[i], 0, sizeof(hwbrj_stats_t));
+        uint64_t rb, rc, sb, sc_;
+        chunk_of(nR, G, i, rb, rc);
+        chunk_of(nS, G, i, sb, sc_);
+        g.inR.ensure(std::max<uint64_t>(rc, 2) * 8 + 64);
+        g.inS.ensure(std::max<uint64_t>(sc_, 2) * 8 + 64);
+        CK(cudaEventRecord(g.ev[9], g.stream));
+        h2d(g.inR.p, relR->tuples + rb, rc * 8);
+        h2d(g.inS.p, relS->tuples + sb, sc_ * 8);
+        CK(cudaEventRecord(g.ev[10], g.stream));
+        sts[i].h2d_bytes = (rc + sc_) * 8;
+    }
+    for (int i = 0; i < G; i++) {  // ... then every GPU's join is enqueued; the barrier kernels meet on the devices
+        CK(cudaSetDevice(i));
+        init_ctx();
+        uint64_t rb, rc, sb, sc_;
+        chunk_of(nR, G, i, rb, rc);
+        chunk_of(nS, G, i, sb, sc_);
+        run_join(g_group[i]->fab, g.inR.as<uint2>(), rc, g.inS.as<uint2>(), sc_, args, nR, sts[i], nullptr, kEnqueue);
+    }
+    int rc_all = 0;
+    hwbrj_stats_t st = sts[0];
+    for (int i = 0; i < G; i++) {
+        CK(cudaSetDevice(i));
+        init_ctx();
+        rc_all |= collect_join(sts[i], args != nullptr);
+        CK(cudaEventElapsedTime(&sts[i].ms_h2d, g.ev[9], g.ev[10]));
+        if (i == 0) st = sts[0];
+        st.ms_total = std::max(st.ms_total, sts[i].ms_total);  // device time, max over the GPUs
+        st.ms_h2d = std::max(st.ms_h2d, sts[i].ms_h2d);
+        if (i) {
+            st.h2d_bytes += sts[i].h2d_bytes;
+            st.d2h_bytes += sts[i].d2h_bytes;
+            st.kernel_launches += sts[i].kernel_launches;
+            st.owned_r = std::max(st.owned_r, sts[i].owned_r);  // the most loaded GPU
+            st.owned_s = std::max(st.owned_s, sts[i].owned_s);
+        }
+    }
+    CK(cudaSetDevice(home));
+    init_ctx();
+    if (rc_all) die("multi-GPU join failed: a receive buffer overflowed or a GPU did not reach a barrier");
+    st.ms_e2e = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    g.last = st;
+    print_reference_lines(st, nS, args != nullptr && print_filtered);
+    result_t* res = (result_t*)malloc(sizeof(result_t));
+    if (!res) die("malloc(result_t) failed");
+    res->totalresults = st.matches;
+    res->resultlist = nullptr;
+    res->nthreads = nthreads;
+    return res;
+}
+
 static result_t* host_join(relation_t* relR, relation_t* relS, int nthreads, bloom_filter_args_t* args,
                            bool print_filtered) {
-    std::lock_guard<std::mutex> lock(g.mu);
+    std::lock_guard<std::recursive_mutex> lock(g_mu);
     init_ctx();
     if (!relR || !relS) die("NULL relation");
+    if (args && check_args_impl(args, true)) die("invalid Bloom filter arguments");
+    if (g_gpus > 1) return host_join_multi(relR, relS, nthreads, args, print_filtered);
     auto t0 = std::chrono::steady_clock::now();
     hwbrj_stats_t st;
     memset(&st, 0, sizeof(st));
     const uint64_t nR = relR->num_tuples, nS = relS->num_tuples;
-    g.inR.ensure(std::max<uint64_t>(nR, 2) * 8);
-    g.inS.ensure(std::max<uint64_t>(nS, 2) * 8);
+    g.inR.ensure(std::max<uint64_t>(nR, 2) * 8 + 64);
+    g.inS.ensure(std::max<uint64_t>(nS, 2) * 8 + 64);
     st.h2d_bytes = (nR + nS) * 8;
+    const Fab f = single_fab();
     if (g.overlap_h2d && args && nS >= (1u << 22)) {
         // copies on their own stream; R first, then S in <= 64 chunks, each followed by an event the probe waits on
         SFeed feed;
@@ -682,7 +1002,7 @@ static result_t* host_join(relation_t* relR, relation_t* relS, int nthreads, blo
         feed.chunk_tuples = (((nS + feed.nchunks - 1) / feed.nchunks) + 1) & ~1ull;  // even: chunks stay 16-byte aligned
         feed.nchunks = (int)((nS + feed.chunk_tuples - 1) / feed.chunk_tuples);
         feed.ev = g.ev_chunk + 1;
-        CK(cudaEventRecord(g.ev[7], g.copy_stream));
+        CK(cudaEventRecord(g.ev_copy[0], g.copy_stream));
         if (nR) CK(cudaMemcpyAsync(g.inR.p, relR->tuples, nR * 8, cudaMemcpyHostToDevice, g.copy_stream));
         CK(cudaEventRecord(g.ev_chunk[0], g.copy_stream));
         for (int c = 0; c < feed.nchunks; c++) {
@@ -691,18 +1011,19 @@ static result_t* host_join(relation_t* relR, relation_t* relS, int nthreads, blo
             CK(cudaMemcpyAsync(g.inS.as<uint2>() + off, relS->tuples + off, cnt * 8, cudaMemcpyHostToDevice, g.copy_stream));
             CK(cudaEventRecord(feed.ev[c], g.copy_stream));
         }
-        CK(cudaEventRecord(g.ev_side[3], g.copy_stream));
+        CK(cudaEventRecord(g.ev_copy[1], g.copy_stream));
         CK(cudaStreamWaitEvent(g.stream, g.ev_chunk[0], 0));  // the R phase needs all of R
-        run_join(g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, st, nullptr, 0, nullptr, &feed);
-        CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[7], g.ev_side[3]));
+        run_join(f, g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, nR, st, &feed);
+        CK(cudaEventSynchronize(g.ev_copy[1]));  // recorded on the copy stream: make sure it has completed before reading it
+        CK(cudaEventElapsedTime(&st.ms_h2d, g.ev_copy[0], g.ev_copy[1]));
     } else {
-        CK(cudaEventRecord(g.ev[7], g.stream));
+        CK(cudaEventRecord(g.ev[9], g.stream));
         h2d(g.inR.p, relR->tuples, nR * 8);
         h2d(g.inS.p, relS->tuples, nS * 8);
-        CK(cudaEventRecord(g.ev[0], g.stream));
+        CK(cudaEventRecord(g.ev[10], g.stream));
         CK(cudaStreamSynchronize(g.stream));
-        CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[7], g.ev[0]));
-        run_join(g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, st);
+        CK(cudaEventElapsedTime(&st.ms_h2d, g.ev[9], g.ev[10]));
+        run_join(f, g.inR.as<uint2>(), nR, g.inS.as<uint2>(), nS, args, nR, st);
     }
     st.ms_e2e = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     g.last = st;
@@ -748,29 +1069,65 @@ result_t* RJ(relation_t* relR, relation_t* relS, int nthreads) {
 }
 
 // ---- Part 2: extensions ---------------------------------------------------------------------------------------
+#define HWBRJ_ENTER() std::lock_guard<std::recursive_mutex> lock_(g_mu); init_ctx()
+
 int hwbrj_last_stats(hwbrj_stats_t* out) {
+    HWBRJ_ENTER();
     if (!out) return -1;
     *out = g.last;
     return 0;
 }
-int64_t hwbrj_last_filtered(void) { return g.last.filtered; }
+int64_t hwbrj_last_filtered(void) {
+    HWBRJ_ENTER();
+    return g.last.filtered;
+}
 int hwbrj_last_filter(unsigned char* bitmap_out, uint64_t nbytes) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!bitmap_out || nbytes > g.filter.cap) return -1;
-    CK(cudaMemcpy(bitmap_out, g.filter.p, nbytes, cudaMemcpyDeviceToHost));
+    HWBRJ_ENTER();
+    const void* src = g_group.empty() ? g.filter.p : (const void*)(g_group[g.dev < (int)g_group.size() ? g.dev : 0]->base +
+                                                                   g_group[0]->off_filter);
+    const uint64_t cap = g_group.empty() ? g.filter.cap : g_group[0]->filter_bytes;
+    if (!bitmap_out || nbytes > cap || !src) return -1;
+    CK(cudaMemcpy(bitmap_out, src, nbytes, cudaMemcpyDeviceToHost));
     return 0;
 }
-uint64_t hwbrj_last_checksum(void) { return g.last.checksum_pair; }
-void hwbrj_set_quiet(int quiet) { g.quiet = quiet != 0; }
-void hwbrj_set_radix_bits(int bits) { g.radix_bits_override = bits; }
-void hwbrj_set_range_passes(int passes) { g.range_passes_override = passes; }
-void hwbrj_set_overlap_h2d(int on) { g.overlap_h2d = on != 0; }
-void hwbrj_set_hash_partition(int mode) {
-    g.hash_partition = mode != 0;
-    g.hash_partition_force = mode == 2;
+uint64_t hwbrj_last_checksum(void) {
+    HWBRJ_ENTER();
+    return g.last.checksum_pair;
 }
-const char* hwbrj_version(void) { return "hwbrj-b200 0.1 (sm_100a)"; }
+void hwbrj_set_quiet(int quiet) { g_quiet = quiet != 0; }
+void hwbrj_set_radix_bits(int bits) {
+    HWBRJ_ENTER();
+    g.radix_bits_override = bits;
+}
+void hwbrj_set_num_passes(int passes) {
+    HWBRJ_ENTER();
+    g.passes_override = passes;
+}
+void hwbrj_set_range_passes(int passes) {
+    HWBRJ_ENTER();
+    g.range_passes_override = passes;
+}
+void hwbrj_set_overlap_h2d(int on) {
+    HWBRJ_ENTER();
+    g.overlap_h2d = on != 0;
+}
+void hwbrj_set_hash_partition(int mode) {
+    HWBRJ_ENTER();
+    g.hash_partition = std::max(0, std::min(2, mode));
+}
+int hwbrj_set_gpus(int n) {
+    std::lock_guard<std::recursive_mutex> lock(g_mu);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (n < 1 || n > ndev || n > kMaxPeers || (n & (n - 1))) return -1;
+    if (n != g_gpus && !g_group.empty()) group_release();
+    g_gpus = n;
+    return 0;
+}
+const char* hwbrj_version(void) { return "hwbrj-b200 0.2 (sm_100a)"; }
 int hwbrj_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -783,20 +1140,15 @@ int hwbrj_check_args(const bloom_filter_args_t* args) { return args ? check_args
 
 struct hwbrj_rel {
     uint2* d;
-    uint64_t n;                        // tuple count, or capacity / upper bound when n_dev is set
+    uint64_t n;
     bool owned;
-    const unsigned long long* n_dev;   // optional: the real count lives on the device (no host round trip)
-    uint64_t n_expect;                 // sizing hint when n_dev is set
 };
 
 hwbrj_rel_t* hwbrj_rel_upload(const tuple_t* tuples, uint64_t n) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     hwbrj_rel_t* r = new hwbrj_rel;
     r->n = n;
     r->owned = true;
-    r->n_dev = nullptr;
-    r->n_expect = n;
     CK(cudaMalloc(&r->d, std::max<uint64_t>(n, 2) * 8 + 64));
     if (n) CK(cudaMemcpy(r->d, tuples, n * 8, cudaMemcpyHostToDevice));
     return r;
@@ -808,15 +1160,12 @@ hwbrj_rel_t* hwbrj_rel_generate(int kind, uint64_t n, uint64_t r, double q, uint
 
 hwbrj_rel_t* hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double q, uint64_t seed, uint64_t begin,
                                       uint64_t count) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (begin > n) begin = n;
     if (count > n - begin) count = n - begin;
     hwbrj_rel_t* rel = new hwbrj_rel;
     rel->n = count;
     rel->owned = true;
-    rel->n_dev = nullptr;
-    rel->n_expect = count;
     CK(cudaMalloc(&rel->d, std::max<uint64_t>(count, 2) * 8 + 64));
     if (count && kind == 2) {
         // Zipf foreign keys over the alphabet 1..r with exponent q (create_relation_zipf, generator.c:659-676)
@@ -869,31 +1218,19 @@ hwbrj_rel_t* hwbrj_rel_wrap(void* device_tuples, uint64_t n) {
     r->d = reinterpret_cast<uint2*>(device_tuples);
     r->n = n;
     r->owned = false;
-    r->n_dev = nullptr;
-    r->n_expect = n;
-    return r;
-}
-hwbrj_rel_t* hwbrj_rel_wrap_counted(void* device_tuples, uint64_t capacity, const void* d_count, uint64_t expected) {
-    hwbrj_rel_t* r = hwbrj_rel_wrap(device_tuples, capacity);
-    if (!r) return nullptr;
-    r->n_dev = reinterpret_cast<const unsigned long long*>(d_count);
-    r->n_expect = expected;
     return r;
 }
 void* hwbrj_rel_ptr(const hwbrj_rel_t* rel) { return rel ? rel->d : nullptr; }
 void hwbrj_set_stream(void* cuda_stream) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     g.stream = reinterpret_cast<cudaStream_t>(cuda_stream);  // 0 is a valid handle: the legacy default stream
 }
 void hwbrj_reset_stream(void) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     g.stream = g.own_stream;
 }
 int hwbrj_set_device(int device) {
-    // must precede the first library call of the process (one process per GPU); buffers live on that device
-    if (g.inited && g.dev != device) return -1;
+    // one process per GPU: call before the first library call; the current CUDA device selects the library's context
     if (cudaSetDevice(device) != cudaSuccess) {
         cudaGetLastError();
         return -2;
@@ -901,68 +1238,74 @@ int hwbrj_set_device(int device) {
     return 0;
 }
 int hwbrj_sync(void) {
-    init_ctx();
+    HWBRJ_ENTER();
     CK(cudaStreamSynchronize(g.stream));
     return 0;
 }
 
 int hwbrj_join_device(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, hwbrj_stats_t* out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (!R || !S) return -1;
     hwbrj_stats_t st;
     memset(&st, 0, sizeof(st));
-    run_join(R->d, R->n, S->d, S->n, args, st, R->n_dev, R->n_expect, S->n_dev);
+    const int rc = run_join(single_fab(), R->d, R->n, S->d, S->n, args, R->n, st);
     g.last = st;
     if (out) *out = st;
-    return 0;
+    return rc;
 }
 
-int hwbrj_join_device_async(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out6) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!R || !S || !d_out6) return -1;
+int hwbrj_join_device_async(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out8) {
+    HWBRJ_ENTER();
+    if (!R || !S || !d_out8) return -1;
     hwbrj_stats_t st;
     memset(&st, 0, sizeof(st));
-    run_join(R->d, R->n, S->d, S->n, args, st, R->n_dev, R->n_expect, S->n_dev, nullptr,
-             reinterpret_cast<unsigned long long*>(d_out6));
+    run_join(single_fab(), R->d, R->n, S->d, S->n, args, R->n, st, nullptr, kCapture,
+             reinterpret_cast<unsigned long long*>(d_out8));
     return st.kernel_launches;
 }
 
-int hwbrj_join_prepare_r(const hwbrj_rel_t* R) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!R || R->n >= (1ull << 32) - (1ull << 20)) return -1;
-    ensure_workspace(R->n, 1, nullptr);
-    const int bits = pick_bits(R->n_dev ? R->n_expect : R->n);
-    const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
-    const uint32_t P = 1u << bits;
-    BloomParams bp;
-    memset(&bp, 0, sizeof(bp));
-    // fork from the caller's stream: everything R depends on has been enqueued there
-    CK(cudaEventRecord(g.ev_prep_fork, g.stream));
-    CK(cudaStreamWaitEvent(g.side_stream, g.ev_prep_fork, 0));
-    CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.side_stream));
-    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + kCrcSmemWords) * 4), g.side_stream>>>(
-        R->d, R->n, R->n_dev, bp, g.d_crc, g.histR.as<uint32_t>(), P - 1u);
-    int launches = 1;
-    g.prep.Rp = run_partition(R->d, R->n, R->n_dev, bits, b2, g.histR.as<uint32_t>(), g.offR.as<uint32_t>(),
-                              g.rt1.as<uint2>(), g.rp.as<uint2>(), launches, g.side_stream, true);
-    CK(cudaEventRecord(g.ev_prep_done, g.side_stream));
-    CK(cudaGetLastError());
-    g.prep.valid = true;
-    g.prep.d = R->d;
-    g.prep.n = R->n;
-    g.prep.n_dev = R->n_dev;
-    g.prep.bits = bits;
-    g.prep.launches = launches;
-    return launches;
+// ---- the multi-GPU join below the C ABI ---------------------------------------------------------------
+hwbrj_dist_t* hwbrj_dist_create(int rank, int world, uint64_t cap_r, uint64_t cap_s, uint64_t max_filter_bytes,
+                                void* handle_out) {
+    HWBRJ_ENTER();
+    return dist_create(rank, world, cap_r, cap_s, max_filter_bytes, handle_out);
 }
+int hwbrj_dist_connect(hwbrj_dist_t* d, const void* all_handles) {
+    HWBRJ_ENTER();
+    if (!d || !all_handles) return -1;
+    return dist_connect(d, all_handles);
+}
+void hwbrj_dist_destroy(hwbrj_dist_t* d) {
+    HWBRJ_ENTER();
+    if (d) CK(cudaDeviceSynchronize());
+    dist_destroy(d);
+}
+int hwbrj_dist_join(hwbrj_dist_t* d, const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args,
+                    uint64_t r_total, hwbrj_stats_t* out) {
+    HWBRJ_ENTER();
+    if (!d || !d->connected || !R || !S) return -1;
+    hwbrj_stats_t st;
+    memset(&st, 0, sizeof(st));
+    const int rc = run_join(d->fab, R->d, R->n, S->d, S->n, args, r_total, st);
+    g.last = st;
+    if (out) *out = st;
+    return rc;
+}
+int hwbrj_dist_join_async(hwbrj_dist_t* d, const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args,
+                          uint64_t r_total, void* d_out8) {
+    HWBRJ_ENTER();
+    if (!d || !d->connected || !R || !S || !d_out8) return -1;
+    hwbrj_stats_t st;
+    memset(&st, 0, sizeof(st));
+    run_join(d->fab, R->d, R->n, S->d, S->n, args, r_total, st, nullptr, kCapture, reinterpret_cast<unsigned long long*>(d_out8));
+    return st.kernel_launches;
+}
+void* hwbrj_dist_filter(hwbrj_dist_t* d) { return d ? d->base + d->off_filter : nullptr; }
 
 void* hwbrj_host_alloc(uint64_t bytes) {
-    init_ctx();
+    HWBRJ_ENTER();
     void* p = nullptr;
-    CK(cudaHostAlloc(&p, std::max<uint64_t>(bytes, 8), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&p, std::max<uint64_t>(bytes, 8), cudaHostAllocPortable));
     return p;
 }
 void hwbrj_host_free(void* p) {
@@ -970,8 +1313,7 @@ void hwbrj_host_free(void* p) {
 }
 
 int hwbrj_hash_many(int which, uint32_t seed, const int32_t* keys, uint64_t n, uint32_t* out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (which < 0 || which > 9) return -1;
     if (!n) return 0;
     g.scratch.ensure(n * 8);
@@ -985,26 +1327,41 @@ int hwbrj_hash_many(int which, uint32_t seed, const int32_t* keys, uint64_t n, u
     return 0;
 }
 
-int hwbrj_bloom_build(const tuple_t* R, uint64_t nR, const bloom_filter_args_t* args, uint32_t seed,
-                      unsigned char* bitmap_out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!args || check_args_impl(args, true)) return -1;
-    g.inR.ensure(std::max<uint64_t>(nR, 2) * 8);
-    g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
+// insert R's keys into the filter at d_filter with global atomics (K1 without a histogram of its own: one bin)
+static void enqueue_filter_build(const uint2* dR, uint64_t n, const bloom_filter_args_t* args, uint32_t seed, void* d_filter) {
     g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
-    h2d(g.inR.p, R, nR * 8);
-    CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
     CK(cudaMemsetAsync(g.histR.p, 0, 4, g.stream));
-    BloomParams bp = make_bloom(args, seed, g.filter.as<uint32_t>());
-    int nranges = pick_ranges(args);
-    bp.nranges = (uint32_t)nranges;
-    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
+    BloomParams bp = make_bloom(args, seed, reinterpret_cast<uint32_t*>(d_filter));
+    const int nranges = pick_ranges(args);
+    set_ranges(bp, args, nranges);
+    PartFn pf;
+    memset(&pf, 0, sizeof(pf));
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(g.inR.as<uint2>(), nR, nullptr, bp, g.d_crc,
-                                                                          g.histR.as<uint32_t>(), 0u);
+        k_build_hist<true, 0><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(dR, n, nullptr, bp, g.d_crc,
+                                                                                  g.histR.as<uint32_t>(), pf);
     }
+}
+// probe S against the filter at d_filter; survivors to d_out, their number to *d_count (zeroed here)
+static void enqueue_filter_probe(const uint2* dS, uint64_t n, const bloom_filter_args_t* args, uint32_t seed,
+                                 const void* d_filter, uint2* d_out, unsigned long long* d_count) {
+    CK(cudaMemsetAsync(d_count, 0, 8, g.stream));
+    BloomParams bp = make_bloom(args, seed, reinterpret_cast<uint32_t*>(const_cast<void*>(d_filter)));
+    const int nranges = pick_ranges(args);
+    set_ranges(bp, args, nranges);
+    run_probe(dS, n, nullptr, bp, nranges, d_out, d_count);
+}
+
+int hwbrj_bloom_build(const tuple_t* R, uint64_t nR, const bloom_filter_args_t* args, uint32_t seed,
+                      unsigned char* bitmap_out) {
+    HWBRJ_ENTER();
+    if (!args || check_args_impl(args, true)) return -1;
+    invalidate_last();
+    g.inR.ensure(std::max<uint64_t>(nR, 2) * 8 + 64);
+    g.filter.ensure(std::max<uint64_t>(args->m / 8, 16));
+    h2d(g.inR.p, R, nR * 8);
+    CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 16), g.stream));
+    enqueue_filter_build(g.inR.as<uint2>(), nR, args, seed, g.filter.p);
     CK(cudaMemcpyAsync(bitmap_out, g.filter.p, args->m / 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaGetLastError());
@@ -1013,27 +1370,17 @@ int hwbrj_bloom_build(const tuple_t* R, uint64_t nR, const bloom_filter_args_t* 
 
 int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_t nS, const bloom_filter_args_t* args,
                           uint32_t seed, tuple_t* survivors_out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (!args || check_args_impl(args, true)) return -1;
-    g.inS.ensure(std::max<uint64_t>(nS, 2) * 8);
-    g.sc.ensure(std::max<uint64_t>(nS, 1) * 8);
-    g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
-    g.histS.ensure(((size_t)1 << kMaxRadixBits) * 4);
+    invalidate_last();
+    g.inS.ensure(std::max<uint64_t>(nS, 2) * 8 + 64);
+    g.sc.ensure(std::max<uint64_t>(nS, 1) * 8 + 64);
+    g.filter.ensure(std::max<uint64_t>(args->m / 8, 16));
     g.ctrl.ensure(sizeof(Control));
     h2d(g.inS.p, S, nS * 8);
     h2d(g.filter.p, bitmap, args->m / 8);
-    CK(cudaMemsetAsync(g.histS.p, 0, 4, g.stream));
-    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
     Control* ctrl = g.ctrl.as<Control>();
-    BloomParams bp = make_bloom(args, seed, g.filter.as<uint32_t>());
-    int nranges = pick_ranges(args);
-    bp.nranges = (uint32_t)nranges;
-    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    g.st1.ensure(std::max<uint64_t>(nS, 1) * 8);
-    if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(nS, 1) * 8);
-    run_probe(g.inS.as<uint2>(), nS, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(),
-              nranges > 2 ? g.d1.as<uint2>() : nullptr);
+    enqueue_filter_probe(g.inS.as<uint2>(), nS, args, seed, g.filter.p, g.sc.as<uint2>(), &ctrl->survivors);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -1045,7 +1392,8 @@ int64_t hwbrj_bloom_probe(const unsigned char* bitmap, const tuple_t* S, uint64_
 // Materialise the output of the most recent join: re-runs only the per-partition build+probe (K5) over the
 // partitions that join left in the workspace, writing one {R.payload, S.payload} tuple per match
 // (bucket_chaining_join under JOIN_RESULT_MATERIALIZE, :307-312). Returns the number of pairs (which may exceed
-// `capacity`: then only the first `capacity` slots were written and the caller retries with a larger buffer).
+// `capacity`: then only the first `capacity` slots were written and the caller retries with a larger buffer), or -1 when
+// there is no join to materialise: any other call that touches the workspace invalidates it.
 static int64_t materialize_last(uint2* d_pairs, uint64_t capacity) {
     if (!g.last_Rp || !g.last_Sp) return -1;
     Control* ctrl = g.ctrl.as<Control>();
@@ -1069,47 +1417,36 @@ static int64_t materialize_last(uint2* d_pairs, uint64_t capacity) {
 }
 
 int64_t hwbrj_materialize_last(tuple_t* pairs_out, uint64_t capacity) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (!pairs_out && capacity) return -1;
-    g.pairs.ensure(std::max<uint64_t>(capacity, 1) * 8);
+    if (!g.last_Rp || !g.last_Sp) return -1;
+    const uint2 *keepR = g.last_Rp, *keepS = g.last_Sp;
+    g.pairs.ensure(std::max<uint64_t>(capacity, 1) * 8);  // its re-allocation does not touch the partitions
+    g.last_Rp = keepR;
+    g.last_Sp = keepS;
     int64_t n = materialize_last(g.pairs.as<uint2>(), capacity);
     if (n > 0) CK(cudaMemcpy(pairs_out, g.pairs.p, std::min<uint64_t>((uint64_t)n, capacity) * 8, cudaMemcpyDeviceToHost));
     return n;
 }
 
 int64_t hwbrj_materialize_last_device(void* d_pairs, uint64_t capacity) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     return materialize_last(reinterpret_cast<uint2*>(d_pairs), capacity);
 }
 
 // device analogue of the reference's FPR measurement (test_bloom_fpr, unit_tests.c:191-241): build a filter with the
 // given seed from R, probe S, return how many S keys pass
 int64_t hwbrj_fpr_count(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_filter_args_t* args, uint32_t seed) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (!R || !S || !args || check_args_impl(args, true)) return -1;
-    g.filter.ensure(std::max<uint64_t>(args->m / 8, 4));
-    g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
-    g.sc.ensure(std::max<uint64_t>(S->n, 1) * 8);
-    g.st1.ensure(std::max<uint64_t>(S->n, 1) * 8);
+    invalidate_last();
+    g.filter.ensure(std::max<uint64_t>(args->m / 8, 16));
+    g.sc.ensure(std::max<uint64_t>(S->n, 1) * 8 + 64);
     g.ctrl.ensure(sizeof(Control));
-    CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
-    CK(cudaMemsetAsync(g.histR.p, 0, 4, g.stream));
-    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
+    CK(cudaMemsetAsync(g.filter.p, 0, std::max<uint64_t>(args->m / 8, 16), g.stream));
     Control* ctrl = g.ctrl.as<Control>();
-    BloomParams bp = make_bloom(args, seed, g.filter.as<uint32_t>());
-    int nranges = pick_ranges(args);
-    bp.nranges = (uint32_t)nranges;
-    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    for (int r = 0; r < nranges; r++) {
-        bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, R->n_dev, bp, g.d_crc,
-                                                                                  g.histR.as<uint32_t>(), 0u);
-    }
-    if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(S->n, 1) * 8);
-    run_probe(S->d, S->n, bp, nranges, g.sc.as<uint2>(), ctrl, g.st1.as<uint2>(), nranges > 2 ? g.d1.as<uint2>() : nullptr);
+    enqueue_filter_build(R->d, R->n, args, seed, g.filter.p);
+    enqueue_filter_probe(S->d, S->n, args, seed, g.filter.p, g.sc.as<uint2>(), &ctrl->survivors);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -1117,23 +1454,38 @@ int64_t hwbrj_fpr_count(const hwbrj_rel_t* R, const hwbrj_rel_t* S, const bloom_
     return (int64_t)cnt;
 }
 
-int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out, uint64_t* offsets) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (bits < 0 || bits > kMaxRadixBits || n >= (1ull << 32)) return -1;
-    ensure_workspace(n, 1, nullptr);
-    g.inR.ensure(std::max<uint64_t>(n, 2) * 8);
-    const uint32_t P = 1u << bits;
-    const int b2 = bits > kMaxLevelBits ? bits / 2 : 0;
-    h2d(g.inR.p, in, n * 8);
+// partition `in` (device, n tuples) with the pipeline's own kernels into t-buffers of the workspace; returns the result
+static const uint2* partition_local(int pmode, const PartFn& pf, const uint2* in, uint64_t n, int& launches) {
+    ensure_workspace(n, 1, 1, nullptr, false);
+    Control* ctrl = g.ctrl.as<Control>();
+    const uint32_t P = 1u << pf.bits;
     CK(cudaMemsetAsync(g.histR.p, 0, P * 4, g.stream));
+    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
-    k_build_hist<false><<<g.sms * 2, 1024, (int)((P + kCrcSmemWords) * 4), g.stream>>>(g.inR.as<uint2>(), n, nullptr, bp, g.d_crc,
-                                                                            g.histR.as<uint32_t>(), P - 1u);
+    launch_hist(pmode, in, n, nullptr, bp, g.histR.as<uint32_t>(), pf);
+    Fab f = single_fab();
+    PeerBufs recv;
+    memset(&recv, 0, sizeof(recv));
+    recv.buf[0] = g.rt1.as<uint2>();
+    recv.shift = pf.bits - pf.b2;
+    return run_partition(f, pmode, pf, in, n, nullptr, g.histR.as<uint32_t>(), f.histR, recv, n, g.offR.as<uint32_t>(),
+                         g.rp.as<uint2>(), &ctrl->n_own_r, ctrl, launches);
+}
+
+int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out, uint64_t* offsets) {
+    HWBRJ_ENTER();
+    if (bits < 0 || bits > kMaxRadixBits || n >= (1ull << 32) - (1ull << 20)) return -1;
+    invalidate_last();
+    g.inR.ensure(std::max<uint64_t>(n, 2) * 8 + 64);
+    const uint32_t P = 1u << bits;
+    h2d(g.inR.p, in, n * 8);
+    PartFn pf;
+    memset(&pf, 0, sizeof(pf));
+    pf.bits = (uint32_t)bits;
+    pf.b2 = (uint32_t)pick_b2(bits, 0);
     int launches = 0;
-    const uint2* res = run_partition(g.inR.as<uint2>(), n, nullptr, bits, b2, g.histR.as<uint32_t>(),
-                                     g.offR.as<uint32_t>(), g.rt1.as<uint2>(), g.rp.as<uint2>(), launches);
+    const uint2* res = partition_local(0, pf, g.inR.as<uint2>(), n, launches);
     std::vector<uint32_t> off32(P + 1);
     if (n) CK(cudaMemcpyAsync(out, res, n * 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaMemcpyAsync(off32.data(), g.offR.p, (P + 1) * 4, cudaMemcpyDeviceToHost, g.stream));
@@ -1143,221 +1495,65 @@ int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out,
     return 0;
 }
 
-}  // extern "C"
-
-// ---- multi-GPU building blocks: the host (hwbloomradixjoin_b200/dist.py, one process per GPU)
-// orchestrates these between torch.distributed collectives; all of them take raw device pointers and run on the
-// stream given to hwbrj_set_stream() ------------------------------------------------------------------------------
-namespace hwbrj {
-static BinFn owner_fn(int world, const bloom_filter_args_t* slice_args, int& mode) {
-    BinFn fn;
-    memset(&fn, 0, sizeof(fn));
-    const int gbits = ilog2_u64((uint64_t)world);
-    fn.seed = 42u;
-    fn.binmask = 0xFFFFFFFFu;
-    if (slice_args && slice_args->variant == BLOCKED) {
-        mode = 4;  // owner = top bits of the block index (all k bits of a key live in that block)
-        uint64_t nblocks = slice_args->m / slice_args->B;
-        fn.size_mask = (uint32_t)(nblocks - 1);
-        fn.oshift = (uint32_t)std::max(0, ilog2_u64(nblocks) - gbits);
-    } else if (slice_args) {
-        mode = 3;  // owner = top bits of the first bit address crapwow & (m-1)
-        fn.size_mask = (uint32_t)(slice_args->m - 1);
-        fn.oshift = (uint32_t)std::max(0, ilog2_u64(slice_args->m) - gbits);
-    } else {
-        mode = 3;  // no sliceable filter: owner = top bits of crapwow(42,key)
-        fn.size_mask = 0xFFFFFFFFu;
-        fn.oshift = (uint32_t)(32 - gbits);
-    }
-    return fn;
-}
-}  // namespace hwbrj
-
-extern "C" {
-
+// ---- building blocks of the NCCL reference path (hwbloomradixjoin_b200/dist.py: dist_join) --------------------------
 int hwbrj_owner_partition(const hwbrj_rel_t* in, int world, const bloom_filter_args_t* slice_args, void* d_out,
                           uint64_t* counts_out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!in || world < 1 || world > 128 || (world & (world - 1)) || in->n >= (1ull << 32)) return -1;
+    HWBRJ_ENTER();
+    if (!in || world < 1 || world > 128 || (world & (world - 1)) || in->n >= (1ull << 32) - (1ull << 20)) return -1;
     if (slice_args && check_args_impl(slice_args, true)) return -1;
     if (slice_args && slice_args->variant == BASIC && slice_args->k > 1) slice_args = nullptr;  // not sliceable
     if (slice_args) {
         uint64_t units = slice_args->variant == BLOCKED ? slice_args->m / slice_args->B : slice_args->m;
         if (units < (uint64_t)world) return -1;
     }
-    ensure_workspace(1, 1, nullptr);
-    int mode = 3;
-    BinFn fn = owner_fn(world, slice_args, mode);
-    const uint32_t nb = (uint32_t)world;
-    CK(cudaMemsetAsync(g.histR.p, 0, nb * 4, g.stream));
-    if (mode == 4)
-        k_owner_hist<4><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, nullptr, fn, g.d_crc, nb, g.histR.as<uint32_t>());
-    else
-        k_owner_hist<3><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, nullptr, fn, g.d_crc, nb, g.histR.as<uint32_t>());
-    k_scan<<<1, 1024, 0, g.stream>>>(g.histR.as<uint32_t>(), nb, 0u, g.offR.as<uint32_t>(), g.cur1.as<uint32_t>(),
-                                     g.cur2.as<uint32_t>(), g.tiles.as<uint32_t>());
-    if (mode == 4)
-        k_scatter<4><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(
-            in->d, reinterpret_cast<uint2*>(d_out), nullptr, in->n, g.offR.as<uint32_t>(), g.tiles.as<uint32_t>(),
-            g.cur1.as<uint32_t>(), fn, g.d_crc, nb);
-    else
-        k_scatter<3><<<g.sms * g.occ_scatter1, kScatterThreads, kScatterSmem, g.stream>>>(
-            in->d, reinterpret_cast<uint2*>(d_out), nullptr, in->n, g.offR.as<uint32_t>(), g.tiles.as<uint32_t>(),
-            g.cur1.as<uint32_t>(), fn, g.d_crc, nb);
-    std::vector<uint32_t> off(nb + 1);
-    CK(cudaMemcpyAsync(off.data(), g.offR.p, (nb + 1) * 4, cudaMemcpyDeviceToHost, g.stream));
+    invalidate_last();
+    // owner = the rank holding the filter slice of the key's first bit / block; without a sliceable filter the top bits of
+    // crapwow(42, key). Equal keys share an owner.
+    const int gbits = ilog2_u64((uint64_t)world);
+    PartFn pf;
+    memset(&pf, 0, sizeof(pf));
+    pf.bits = (uint32_t)gbits;
+    pf.seed = 42u;
+    int pmode = 1;
+    if (slice_args && slice_args->variant == BLOCKED) {
+        pmode = 2;
+        const uint64_t nblocks = slice_args->m / slice_args->B;
+        pf.size_mask = (uint32_t)(nblocks - 1);
+        pf.hshift = (uint32_t)(ilog2_u64(nblocks) - gbits);
+    } else if (slice_args) {
+        pf.size_mask = (uint32_t)(slice_args->m - 1);
+        pf.hshift = (uint32_t)(ilog2_u64(slice_args->m) - gbits);
+    } else {
+        pf.size_mask = gbits ? 0xFFFFFFFFu : 0u;  // one rank: everything is partition 0 (no 32-bit shift)
+        pf.hshift = gbits ? (uint32_t)(32 - gbits) : 0u;
+    }
+    if (pf.hshift > 31u) {  // world == 1 with a one-unit filter
+        pf.size_mask = 0u;
+        pf.hshift = 0u;
+    }
+    int launches = 0;
+    const uint2* res = partition_local(pmode, pf, in->d, in->n, launches);
+    std::vector<uint32_t> off((size_t)world + 1);
+    if (in->n) CK(cudaMemcpyAsync(d_out, res, in->n * 8, cudaMemcpyDeviceToDevice, g.stream));
+    CK(cudaMemcpyAsync(off.data(), g.offR.p, ((size_t)world + 1) * 4, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaGetLastError());
-    for (uint32_t i = 0; i < nb; i++) counts_out[i] = off[i + 1] - off[i];
-    return 0;
-}
-
-// ---- peer memory (CUDA IPC) and the fused partition + all-to-all ---------------------------------------------------
-void* hwbrj_symm_alloc(uint64_t bytes) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    void* p = nullptr;
-    CK(cudaMalloc(&p, std::max<uint64_t>(bytes, 256)));
-    CK(cudaMemset(p, 0, std::max<uint64_t>(bytes, 256)));
-    return p;
-}
-void hwbrj_symm_free(void* p) {
-    if (p) cudaFree(p);
-}
-int hwbrj_ipc_export(void* p, void* handle_out) {
-    init_ctx();
-    cudaIpcMemHandle_t h;
-    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
-        cudaGetLastError();
-        return -1;
-    }
-    static_assert(sizeof(h) == HWBRJ_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
-    memcpy(handle_out, &h, sizeof(h));
-    return 0;
-}
-void* hwbrj_ipc_open(const void* handle) {
-    init_ctx();
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle, sizeof(h));
-    void* p = nullptr;
-    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    return p;
-}
-int hwbrj_ipc_close(void* p) {
-    if (p && cudaIpcCloseMemHandle(p) != cudaSuccess) {
-        cudaGetLastError();
-        return -1;
-    }
-    return 0;
-}
-
-int hwbrj_route_peer(const hwbrj_rel_t* in, int world, const bloom_filter_args_t* slice_args, void* const* peer_bufs,
-                     void* const* peer_cursors, uint64_t capacity_tuples, void* d_overflow_flag) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!in || world < 1 || world > kMaxPeers || (world & (world - 1)) || in->n >= (1ull << 32)) return -1;
-    if (slice_args && check_args_impl(slice_args, true)) return -1;
-    if (slice_args && slice_args->variant == BASIC && slice_args->k > 1) slice_args = nullptr;
-    ensure_workspace(1, 1, nullptr);
-    int mode = 3;
-    BinFn fn = owner_fn(world, slice_args, mode);
-    PeerTargets pt;
-    memset(&pt, 0, sizeof(pt));
-    for (int i = 0; i < world; i++) {
-        pt.buf[i] = reinterpret_cast<uint2*>(peer_bufs[i]);
-        pt.cursor[i] = reinterpret_cast<unsigned long long*>(peer_cursors[i]);
-    }
-    pt.capacity = capacity_tuples;
-    pt.overflow = reinterpret_cast<unsigned int*>(d_overflow_flag);
-    const uint64_t* n_ptr = reinterpret_cast<const uint64_t*>(in->n_dev);
-    static int occ3 = 0, occ4 = 0;
-    if (!occ3) {
-        CK(cudaFuncSetAttribute(k_scatter<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-        CK(cudaFuncSetAttribute(k_scatter<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_scatter<3, true>, kScatterThreads, kScatterSmem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_scatter<4, true>, kScatterThreads, kScatterSmem));
-        occ3 = std::max(occ3, 1);
-        occ4 = std::max(occ4, 1);
-    }
-    if (g.route_precount) {  // experimental: one remote claim per owner instead of one per (tile, owner)
-        g.route_hist.ensure(kMaxPeers * sizeof(uint32_t));
-        g.route_cur.ensure(kMaxPeers * sizeof(unsigned long long));
-        CK(cudaMemsetAsync(g.route_hist.p, 0, kMaxPeers * sizeof(uint32_t), g.stream));
-        if (mode == 4)
-            k_owner_hist<4><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, in->n_dev, fn, g.d_crc, (uint32_t)world,
-                                                             g.route_hist.as<uint32_t>());
-        else
-            k_owner_hist<3><<<g.sms * 4, 256, 0, g.stream>>>(in->d, in->n, in->n_dev, fn, g.d_crc, (uint32_t)world,
-                                                             g.route_hist.as<uint32_t>());
-        k_route_claim<<<1, 32, 0, g.stream>>>(g.route_hist.as<uint32_t>(), pt, (uint32_t)world,
-                                              g.route_cur.as<unsigned long long>());
-        for (int i = 0; i < world; i++) pt.cursor[i] = g.route_cur.as<unsigned long long>() + i;  // local sub-allocation
-    }
-    if (mode == 4)
-        k_scatter<4, true><<<g.sms * occ4, kScatterThreads, kScatterSmem, g.stream>>>(
-            in->d, nullptr, n_ptr, in->n, nullptr, nullptr, nullptr, fn, g.d_crc, (uint32_t)world, pt);
-    else
-        k_scatter<3, true><<<g.sms * occ3, kScatterThreads, kScatterSmem, g.stream>>>(
-            in->d, nullptr, n_ptr, in->n, nullptr, nullptr, nullptr, fn, g.d_crc, (uint32_t)world, pt);
-    CK(cudaGetLastError());
-    return 0;
-}
-
-// probe that leaves the survivor count on the device (no host round trip): count_out is a device u64, zeroed here
-int hwbrj_filter_probe_async(const void* d_filter, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out,
-                             void* d_count_out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
-    if (!S || !args || !d_filter || !d_out || !d_count_out || check_args_impl(args, true)) return -1;
-    g.ctrl.ensure(sizeof(Control));
-    g.st1.ensure(std::max<uint64_t>(S->n, 1) * 8);
-    CK(cudaMemsetAsync(d_count_out, 0, 8, g.stream));
-    BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(const_cast<void*>(d_filter)));
-    int nranges = pick_ranges(args);
-    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    const int base_mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0);
-    bp.nranges = (uint32_t)nranges;
-    for (int r = 0; r < nranges; r++) {
-        bp.range_id = (uint32_t)r;
-        launch_probe_mode(base_mode | (nranges > 1 ? 4 : 0), S->d, S->n, S->n_dev, bp, reinterpret_cast<uint2*>(d_out),
-                          reinterpret_cast<unsigned long long*>(d_count_out), nullptr, nullptr);
-    }
-    CK(cudaGetLastError());
+    for (int i = 0; i < world; i++) counts_out[i] = off[i + 1] - off[i];
     return 0;
 }
 
 int hwbrj_filter_build(const hwbrj_rel_t* R, const bloom_filter_args_t* args, void* d_filter, int zero_first) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (!R || !args || !d_filter || check_args_impl(args, true)) return -1;
-    g.histR.ensure(((size_t)1 << kMaxRadixBits) * 4);
-    // the (unused) one-bin histogram of the insert kernel: histR, unless a prepared R partitioning owns histR right now
-    uint32_t* hist = g.histR.as<uint32_t>();
-    if (g.prep.valid) {
-        g.histF.ensure(256);
-        hist = g.histF.as<uint32_t>();
-    }
+    invalidate_last();
     if (zero_first) CK(cudaMemsetAsync(d_filter, 0, std::max<uint64_t>(args->m / 8, 4), g.stream));
-    CK(cudaMemsetAsync(hist, 0, 4, g.stream));
-    BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(d_filter));
-    int nranges = pick_ranges(args);
-    bp.nranges = (uint32_t)nranges;
-    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    for (int r = 0; r < nranges; r++) {
-        bp.range_id = (uint32_t)r;
-        k_build_hist<true><<<g.sms * 2, 1024, (1 + kCrcSmemWords) * 4, g.stream>>>(R->d, R->n, R->n_dev, bp, g.d_crc, hist, 0u);
-    }
+    enqueue_filter_build(R->d, R->n, args, 42u, d_filter);
     CK(cudaGetLastError());
     return 0;
 }
 
 int hwbrj_filter_or(void* d_dst, const void* d_src, uint64_t nbytes) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (nbytes % 16) return -1;
     k_filter_or<<<g.sms * 8, 256, 0, g.stream>>>(reinterpret_cast<uint4*>(d_dst), reinterpret_cast<const uint4*>(d_src),
                                                  nbytes / 16);
@@ -1366,20 +1562,12 @@ int hwbrj_filter_or(void* d_dst, const void* d_src, uint64_t nbytes) {
 }
 
 int64_t hwbrj_filter_probe(const void* d_filter, const hwbrj_rel_t* S, const bloom_filter_args_t* args, void* d_out) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    init_ctx();
+    HWBRJ_ENTER();
     if (!S || !args || !d_filter || !d_out || check_args_impl(args, true)) return -1;
+    invalidate_last();
     g.ctrl.ensure(sizeof(Control));
-    CK(cudaMemsetAsync(g.ctrl.p, 0, sizeof(Control), g.stream));
     Control* ctrl = g.ctrl.as<Control>();
-    BloomParams bp = make_bloom(args, 42u, reinterpret_cast<uint32_t*>(const_cast<void*>(d_filter)));
-    int nranges = pick_ranges(args);
-    bp.nranges = (uint32_t)nranges;
-    bp.range_shift = (uint32_t)(ilog2_u64(args->m) - ilog2_u64((uint64_t)nranges));
-    g.st1.ensure(std::max<uint64_t>(S->n, 1) * 8);
-    if (nranges > 2 && g.defer_ranges) g.d1.ensure(std::max<uint64_t>(S->n, 1) * 8);
-    run_probe(S->d, S->n, bp, nranges, reinterpret_cast<uint2*>(d_out), ctrl, g.st1.as<uint2>(),
-              nranges > 2 ? g.d1.as<uint2>() : nullptr);
+    enqueue_filter_probe(S->d, S->n, args, 42u, d_filter, reinterpret_cast<uint2*>(d_out), &ctrl->survivors);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->survivors, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));

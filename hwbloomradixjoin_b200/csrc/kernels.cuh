@@ -44,15 +44,6 @@ constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTil
 #ifndef HWBRJ_PROBE_V
 #define HWBRJ_PROBE_V 4
 #endif
-#ifndef HWBRJ_PROBE_PREFETCH
-#define HWBRJ_PROBE_PREFETCH 0
-#endif
-#ifndef HWBRJ_K2_ABLATE
-#define HWBRJ_K2_ABLATE 0  // TIMING EXPERIMENTS ONLY (results are wrong): 1 = no filter loads, 2 = no shared output cursor
-#endif
-#ifndef HWBRJ_PROBE_CLAIM_AHEAD
-#define HWBRJ_PROBE_CLAIM_AHEAD 0  // round-2 experiment: see WarpRing::claim_if_full
-#endif
 #ifdef HWBRJ_PROBE_MINBLOCKS
 #define HWBRJ_PROBE_BOUNDS __launch_bounds__(kProbeWarps * 32, HWBRJ_PROBE_MINBLOCKS)
 #else
@@ -209,22 +200,40 @@ __global__ void k_hash_many(int which, uint32_t seed, const int32_t* __restrict_
         out[i] = hash_dispatch(which, seed, (uint32_t)keys[i]);
 }
 
-// ---- K1 (+K3 histogram): Bloom insert fused with the radix histogram of R ------------------------------------
+// ---- partition function -------------------------------------------------------------------------------------------
+// A tuple's partition id pid in [0, 2^bits) decides everything downstream: level-1 scatter bin = pid >> b2, level-2 bin =
+// pid & (2^b2 - 1), owner GPU = pid >> (bits - log2 G), table index inside the partition = the key bits that are left.
+// PMODE 0 (radix): pid = key & (2^bits - 1)                    -- HASH_BIT_MODULO, parallel_radix_join_bloom.c:74
+// PMODE 1 (hash, BASIC filter): pid = (crapwow(seed,key) & (m-1)) >> (log2 m - bits), i.e. the index of the m/2^bits-bit
+//         SLICE of the filter that holds the key's first bit: partition p owns bits [p*m/2^bits, (p+1)*m/2^bits)
+// PMODE 2 (hash, BLOCKED filter): pid = (crc32c(seed,key) & (m/B-1)) >> (log2(m/B) - bits), the slice holding the key's block
+struct PartFn {
+    uint32_t bits, b2;
+    uint32_t seed, size_mask, hshift;  // hash modes; size_mask == 0 (bits == 0) maps everything to partition 0
+};
+template <int PMODE>
+__device__ __forceinline__ uint32_t pid_of(const PartFn& f, const uint32_t* crc_tab, uint32_t key) {
+    if (PMODE == 0) return key & ((1u << f.bits) - 1u);
+    if (PMODE == 1) return (hash_crapwow(f.seed, key) & f.size_mask) >> f.hshift;
+    return (crc32c_tab(crc_tab, f.seed, key) & f.size_mask) >> f.hshift;
+}
+
+// ---- K1 (+K3 histogram): Bloom insert fused with the partition histogram ---------------------------------------
 // replaces the build branch of the histogram loop, parallel_radix_join_bloom.c:794-805 + add_generic
-// (bloom_filter.c:74-89). Also used without a filter (plain PRO histogram, parallel_radix_join.c:770-775).
-// dynamic smem: hist[pmask+1] then crc table[kCrcSmemWords]
-// HASHPID: the partition id is the filter-slice index (crapwow(seed,key) & size_mask) >> hshift instead of key & pmask
-template <bool BLOOM, bool HASHPID = false>
-__global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ rel, uint64_t n_static,
+// (bloom_filter.c:74-89). Also used without a filter (plain PRO histogram, parallel_radix_join.c:770-775) and for the
+// survivors of the probe. dynamic smem: hist[2^bits] then crc table[kCrcSmemWords]
+template <bool BLOOM, int PMODE>
+__global__ void __launch_bounds__(1024, 2) k_build_hist(const uint2* __restrict__ rel, uint64_t n_static,
                                                     const unsigned long long* __restrict__ n_ptr, BloomParams bp,
                                                     const uint32_t* __restrict__ g_crc, uint32_t* __restrict__ ghist,
-                                                    uint32_t pmask, uint32_t hshift = 0) {
+                                                    PartFn pf) {
     extern __shared__ uint32_t smem[];
-    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
+    const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;  // n_static bounds a device-side count
+    const uint32_t P = 1u << pf.bits;
     uint32_t* hist = smem;
-    uint32_t* crc_tab = smem + (pmask + 1u);
-    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) hist[i] = 0u;
-    if (BLOOM && bp.blocked) load_crc_tab(crc_tab, g_crc);
+    uint32_t* crc_tab = smem + P;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0u;
+    if ((BLOOM && bp.blocked) || PMODE == 2) load_crc_tab(crc_tab, g_crc);
     __syncthreads();
     const uint64_t pol = policy_evict_first();
     const uint64_t npairs = n >> 1;
@@ -237,8 +246,7 @@ __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ r
             if (!bloom_in_range(bp, base + h)) return;
             bloom_insert(bp, base, h, y);
         }
-        if (HASHPID) atomicAdd(&hist[(hash_crapwow(bp.seed, key) & bp.size_mask) >> hshift], 1u);
-        else atomicAdd(&hist[key & pmask], 1u);
+        atomicAdd(&hist[pid_of<PMODE>(pf, crc_tab, key)], 1u);
     };
     constexpr int U = 4;  // 128-bit loads in flight per thread
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride * U) {
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ r
     }
     if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) one(rel[n - 1].x);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= pmask; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
         uint32_t c = hist[i];
         if (c) atomicAdd(&ghist[i], c);
     }
@@ -274,12 +282,15 @@ __global__ void __launch_bounds__(1024) k_build_hist(const uint2* __restrict__ r
 // 128-byte lines (claims are multiples of kWarpFlush, so every flush but the last is line-aligned).
 constexpr int kProbeWarps = 8;               // warps per CTA
 
-// per-warp shared-memory ring: tuples are appended with ballot/popc ranks and drained in line-aligned pieces
+// per-warp shared-memory ring: tuples are appended with ballot/popc ranks and drained in line-aligned pieces.
+// (Round-2 measurements, profiles/r2_k2_ablation_and_tuning.log: a private output region per warp instead of the shared
+// cursor changes nothing (5.07 vs 5.00 ms), claiming the output space one iteration ahead is slower (5.18 ms), smaller
+// rings are slower (6.2 ms at 128 tuples) -- the cursor atomic is not what K2 waits for.)
 template <int CAP>  // power of two; drained CAP/2 tuples at a time
 struct WarpRing {
     uint2* buf;
     uint32_t head, count;  // warp-uniform
-    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; pend_base = 0ull; pending = false; priv_next = 0ull; }
+    __device__ __forceinline__ void init(uint2* b) { buf = b; head = 0u; count = 0u; }
     __device__ __forceinline__ void append2(bool fa, uint2 a, bool fb, uint2 b, uint32_t lt) {
         const uint32_t ma = __ballot_sync(0xffffffffu, fa);
         const uint32_t mb = __ballot_sync(0xffffffffu, fb);
@@ -297,49 +308,12 @@ struct WarpRing {
                                           uint32_t lane) {
         __syncwarp();
         unsigned long long gb = 0ull;
-#if HWBRJ_K2_ABLATE & 2
-        gb = priv_next;  // private output region of this warp: measures K2 without the atomic on the shared cursor
-        priv_next += cnt;
-#else
         if (lane == 0) gb = atomicAdd(cursor, (unsigned long long)cnt);
         gb = __shfl_sync(0xffffffffu, gb, 0);
-#endif
         for (uint32_t i = lane; i < cnt; i += 32u) st_stream_v2(out + gb + i, buf[(head + i) & (CAP - 1)], pol);
         head = (head + cnt) & (CAP - 1);
         count -= cnt;
         __syncwarp();
-    }
-    // ---- claim-ahead drains (HWBRJ_PROBE_CLAIM_AHEAD, untested on hardware yet): the output space of a drain is
-    // claimed at the end of one iteration and written at the start of the next, after that iteration's loads have
-    // been issued, so the round trip of the atomic on the shared cursor is hidden. Capacity: fewer than CAP/2 tuples
-    // are left after complete(); if one iteration can append more than CAP/2, make_room() drains in place.
-    unsigned long long priv_next;  // HWBRJ_K2_ABLATE & 2 only
-    unsigned long long pend_base;  // valid in lane 0 while pending
-    bool pending;                  // warp-uniform
-    __device__ __forceinline__ void claim_if_full(unsigned long long* cursor, uint32_t lane) {
-        if (!pending && count >= (uint32_t)(CAP / 2)) {
-            if (lane == 0) pend_base = atomicAdd(cursor, (unsigned long long)(CAP / 2));  // result consumed in complete()
-            pending = true;
-        }
-    }
-    __device__ __forceinline__ void complete(uint2* __restrict__ out, uint64_t pol, uint32_t lane) {
-        if (!pending) return;
-        __syncwarp();
-        const unsigned long long gb = __shfl_sync(0xffffffffu, pend_base, 0);
-        for (uint32_t i = lane; i < (uint32_t)(CAP / 2); i += 32u)
-            st_stream_v2(out + gb + i, buf[(head + i) & (CAP - 1)], pol);
-        head = (head + CAP / 2) & (CAP - 1);
-        count -= CAP / 2;
-        pending = false;
-        __syncwarp();
-    }
-    // claim-ahead safety valve: rings smaller than one iteration's worst case (64 x kProbeV tuples) drain in place
-    // before the next append2 (which adds up to 64) could overflow them
-    __device__ __forceinline__ void make_room(uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol, uint32_t lane) {
-        if (count > (uint32_t)(CAP - 64)) {
-            complete(out, pol, lane);
-            if (count > (uint32_t)(CAP - 64)) drain(CAP / 2, out, cursor, pol, lane);
-        }
     }
     // at most 64 tuples are appended between two calls, so one drain of CAP/2 keeps the ring from overflowing
     __device__ __forceinline__ void drain_if_full(uint2* __restrict__ out, unsigned long long* cursor, uint64_t pol, uint32_t lane) {
@@ -347,29 +321,22 @@ struct WarpRing {
     }
 };
 
-// MODE bit0: BLOCKED, bit1: single probe (k == 1), bit2: range passes active, bit3: DEFER -- compile-time
-// specialisation keeps the per-tuple instruction count down (the kernel is issue- and L1TEX-wavefront-bound).
-// Range passes with deferral: pass i probes the keys whose first filter bit lies in range i (that part of the filter
-// stays L2-resident) and appends the keys of later ranges to `defer_out`, which is the next pass's input -- S is
-// read from HBM once, later passes read only what is still undecided.
+// MODE bit0: BLOCKED, bit1: single probe (k == 1), bit2: range passes active -- compile-time specialisation keeps the
+// per-tuple instruction count down (the kernel is L1TEX-wavefront-bound: one divergent access per SM per clock).
+// Range passes: pass i probes the keys whose first filter bit lies in range i, so that the probed part of the filter
+// stays L2-resident. (Deferring the keys of later ranges to a buffer instead of re-reading S was measured slower in
+// round 1 -- the deferred writes evict the probed range -- and has been removed.)
 #ifndef HWBRJ_PROBE_RING
 #define HWBRJ_PROBE_RING 512  // survivor ring per warp (tuples, power of two >= 128)
 #endif
-__host__ __device__ constexpr int kProbeSmemPerWarp(int mode) {
-    return (mode & 8) ? (256 + 512) * 8 : HWBRJ_PROBE_RING * 8;
-}
+constexpr int kProbeSmemPerWarp = HWBRJ_PROBE_RING * 8;
 template <int MODE>
 __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, uint64_t n_static,
-                                                                   const unsigned long long* __restrict__ n_ptr,
-                                                                   BloomParams bp_in, const uint32_t* __restrict__ g_crc,
-                                                                   uint2* __restrict__ out,
-                                                                   unsigned long long* __restrict__ out_cursor,
-                                                                   uint2* __restrict__ defer_out,
-                                                                   unsigned long long* __restrict__ defer_cursor) {
-    constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0,
-                   kDefer = (MODE & 8) != 0;
-    constexpr int kSurvCap = kDefer ? 256 : HWBRJ_PROBE_RING;
-    static_assert(kSurvCap >= 128, "append2 adds up to 64 tuples between two drain checks");
+                                                   const unsigned long long* __restrict__ n_ptr, BloomParams bp_in,
+                                                   const uint32_t* __restrict__ g_crc, uint2* __restrict__ out,
+                                                   unsigned long long* __restrict__ out_cursor) {
+    constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0;
+    static_assert(HWBRJ_PROBE_RING >= 128, "append2 adds up to 64 tuples between two drain checks");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
     BloomParams bp = bp_in;
@@ -380,120 +347,65 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
         load_crc_tab(crc_tab, g_crc);
         __syncthreads();
     }
-    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
+    const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;  // n_static bounds a device-side count
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    uint2* wsm = reinterpret_cast<uint2*>(smem_raw) + wid * (kProbeSmemPerWarp(MODE) / 8);
-    WarpRing<kSurvCap> surv;
-    surv.init(wsm);
-    WarpRing<512> dfr;
-    dfr.init(wsm + kSurvCap);
+    WarpRing<HWBRJ_PROBE_RING> surv;
+    surv.init(reinterpret_cast<uint2*>(smem_raw) + wid * HWBRJ_PROBE_RING);
     const uint64_t pol = policy_evict_first();
     const uint64_t npairs = n >> 1;
     const uint4* S4 = reinterpret_cast<const uint4*>(S);
     const uint64_t warp_global = (uint64_t)blockIdx.x * kProbeWarps + wid;
     const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
     constexpr uint64_t kPerIter = 32ull * kProbeV;  // pairs per warp iteration
-#if HWBRJ_K2_ABLATE & 2
-    surv.priv_next = warp_global * (n / nwarps);
-#endif
 
-    auto load_batch = [&](uint4 (&dst)[kProbeV], uint64_t it) {
-#pragma unroll
-        for (int j = 0; j < kProbeV; j++) {
-            const uint64_t idx = it * kPerIter + lane + (uint64_t)j * 32u;
-            dst[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
-        }
-    };
-#if HWBRJ_PROBE_PREFETCH
-    uint4 t[kProbeV];
-    if (warp_global * kPerIter < npairs) load_batch(t, warp_global);
-#endif
     for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
         const uint64_t p0 = it * kPerIter + lane;
-#if !HWBRJ_PROBE_PREFETCH
         uint4 t[kProbeV];
-        load_batch(t, it);
-#endif
-        uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
-        bool act[2 * kProbeV], later[2 * kProbeV];
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
-            bool valid = (p0 + (uint64_t)j * 32u) < npairs;
+            const uint64_t idx = p0 + (uint64_t)j * 32u;
+            t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
+        bool act[2 * kProbeV];
+#pragma unroll
+        for (int j = 0; j < kProbeV; j++) {
+            const bool valid = (p0 + (uint64_t)j * 32u) < npairs;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int q = 2 * j + e;
-                uint32_t key = e ? t[j].z : t[j].x;
-                bloom_start(bp, crc_tab, key, base[q], h[q], y[q]);
-                uint32_t a = base[q] + h[q];
-                bool mine = bloom_in_range(bp, a);
-                act[q] = valid && mine;
-                later[q] = kDefer && valid && !mine;  // inputs of pass i only hold ranges >= i
-#if HWBRJ_K2_ABLATE & 1
-                w[q] = 0u;  // no filter traffic: what is left is the S stream, the hashing and the range test
-#else
+                bloom_start(bp, crc_tab, e ? t[j].z : t[j].x, base[q], h[q], y[q]);
+                const uint32_t a = base[q] + h[q];
+                act[q] = valid && bloom_in_range(bp, a);
                 w[q] = act[q] ? ld_filter(bp, bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
-#endif
             }
         }
-#if HWBRJ_PROBE_PREFETCH
-        // the next batch of S is requested while this batch's probes are in flight (out-of-range indices load nothing)
-        uint4 tn[kProbeV];
-        load_batch(tn, it + nwarps);
-#endif
-#if HWBRJ_PROBE_CLAIM_AHEAD
-        if (!kDefer) surv.complete(out, pol, lane);  // the claim was issued an iteration ago: its result is here by now
-#endif
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
-            bool fa = act[2 * j] && (bp.k == 0u || bloom_test_rest(bp, base[2 * j], h[2 * j], y[2 * j], w[2 * j]));
-            bool fb = act[2 * j + 1] &&
-                      (bp.k == 0u || bloom_test_rest(bp, base[2 * j + 1], h[2 * j + 1], y[2 * j + 1], w[2 * j + 1]));
-            const uint2 ta = make_uint2(t[j].x, t[j].y), tb = make_uint2(t[j].z, t[j].w);
-            surv.append2(fa, ta, fb, tb, lt);
-#if HWBRJ_PROBE_CLAIM_AHEAD
-            if (kDefer) surv.drain_if_full(out, out_cursor, pol, lane);
-            else if (64 * kProbeV > kSurvCap / 2) surv.make_room(out, out_cursor, pol, lane);  // compile-time condition
-#else
+            const bool fa = act[2 * j] && (bp.k == 0u || bloom_test_rest(bp, base[2 * j], h[2 * j], y[2 * j], w[2 * j]));
+            const bool fb = act[2 * j + 1] &&
+                            (bp.k == 0u || bloom_test_rest(bp, base[2 * j + 1], h[2 * j + 1], y[2 * j + 1], w[2 * j + 1]));
+            surv.append2(fa, make_uint2(t[j].x, t[j].y), fb, make_uint2(t[j].z, t[j].w), lt);
             surv.drain_if_full(out, out_cursor, pol, lane);
-#endif
-            if (kDefer) {
-                dfr.append2(later[2 * j], ta, later[2 * j + 1], tb, lt);
-                dfr.drain_if_full(defer_out, defer_cursor, pol, lane);
-            }
         }
-#if HWBRJ_PROBE_CLAIM_AHEAD
-        if (!kDefer) surv.claim_if_full(out_cursor, lane);
-#endif
-#if HWBRJ_PROBE_PREFETCH
-#pragma unroll
-        for (int j = 0; j < kProbeV; j++) t[j] = tn[j];
-#endif
     }
-#if HWBRJ_PROBE_CLAIM_AHEAD
-    if (!kDefer) surv.complete(out, pol, lane);
-#endif
     if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
-    if (kDefer && dfr.count) dfr.drain(dfr.count, defer_out, defer_cursor, pol, lane);
     // odd tail tuple
     if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {
-        uint2 tt = S[n - 1];
+        const uint2 tt = S[n - 1];
         uint32_t b0, h0, y0;
         bloom_start(bp, crc_tab, tt.x, b0, h0, y0);
-        uint32_t a = b0 + h0;
-        if (bloom_in_range(bp, a)) {
-            if (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp, bp.filter + (a >> 5)))) {
-                unsigned long long pos = atomicAdd(out_cursor, 1ull);
-                out[pos] = tt;
-            }
-        } else if (kDefer) {
-            unsigned long long pos = atomicAdd(defer_cursor, 1ull);
-            defer_out[pos] = tt;
+        const uint32_t a = b0 + h0;
+        if (bloom_in_range(bp, a) &&
+            (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, ld_filter(bp, bp.filter + (a >> 5))))) {
+            const unsigned long long pos = atomicAdd(out_cursor, 1ull);
+            out[pos] = tt;
         }
     }
 }
 
-// ---- K2 for k >= 2, staged (experimental, HWBRJ_PROBE_STAGED=1; not validated on hardware yet) ------------------------
+// ---- K2 for k >= 2, staged (HWBRJ_PROBE_STAGED=1; parity-checked on hardware in round 2, tests/test_gpu_parity.py) ----
 // With several probes per key the plain kernel walks probes 2..k under divergence: after the first probe 38 % of the
 // lanes are still alive at C1-blocked (k = 4), then 14 %, then 5 %, but the warp pays for every round. Here the keys that
 // pass their FIRST probe are compacted into a per-warp candidate ring (the tuple only), and probes 2..k run on full
@@ -507,7 +419,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
                                                                   unsigned long long* __restrict__ out_cursor) {
     constexpr bool kBlocked = (MODE & 1) != 0, kRanged = (MODE & 4) != 0;
     constexpr int kCandCap = 256, kSurvCap = 256;
-    static_assert((kCandCap + kSurvCap) * 8 == kProbeSmemPerWarp(0) || HWBRJ_PROBE_RING != 512, "smem per warp");
+    static_assert((kCandCap + kSurvCap) * 8 == kProbeSmemPerWarp || HWBRJ_PROBE_RING != 512, "smem per warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
     BloomParams bp = bp_in;
@@ -517,7 +429,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
         load_crc_tab(crc_tab, g_crc);
         __syncthreads();
     }
-    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
+    const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     uint2* wsm = reinterpret_cast<uint2*>(smem_raw) + wid * (kCandCap + kSurvCap);
@@ -598,12 +510,18 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
     }
 }
 
-// ---- K3: exclusive scan of the partition histogram -------------------------------------------------------------
-// replaces the local prefix (:808-811) and the cross-thread offset computation (:819-837).
-// One CTA of 1024 threads; P <= 2^14. Produces fine_off[P+1], level-1 bucket cursors, level-2 cursors and the
-// tile schedule of the level-2 pass (tile_off[P1+1]).
-// Both single-CTA kernels below are pure latency: every thread fetches its (at most 16) bins with independent loads
-// in one round trip, keeps them in registers, and nothing is read back from global memory afterwards.
+// ---- K3: offsets from the partition histograms of all ranks ---------------------------------------------------------
+// replaces the local prefix (:808-811) and the cross-thread offset computation (:819-837); the "threads" of the reference
+// are the G ranks here. One CTA of 1024 threads; P <= 2^14 partitions, of which rank g owns the contiguous range
+// [g*P/G, (g+1)*P/G). hist_all[src][p] = number of tuples of partition p in rank src's input (every rank holds all G
+// rows: they are pushed over NVLink by k_push_rows; G == 1: the row is the local histogram). From these the kernel derives
+//   * send cursors cursor1[B] for every GLOBAL level-1 bin B: this rank's first write position for bin B inside the
+//     receive buffer of B's owner = start of the bin there + tuples the ranks before this one send to it. Every rank
+//     computes the same layout, so the level-1 scatter stores straight into peer memory without any remote atomic;
+//   * for the OWNED partitions: fine_off[PL+1] (boundaries, in increasing pid order -- the reference's cluster order,
+//     :1896-1939), the level-2 cursors, and the tile schedule of the level-2 pass (tile_off[P1L+1]);
+//   * n_own = tuples this rank owns; *abort = 1 if any owner would receive more than `capacity` tuples: then the
+//     scatter kernels store nothing and every partition is declared empty (the join reports the failure).
 constexpr int kBinsPerThread = (1 << kMaxRadixBits) / 1024;
 
 // exclusive block scan of one value per thread (1024 threads); returns the exclusive prefix, total via warp_sums[32]
@@ -632,93 +550,170 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t local, ui
     return warp_sums[wid] + inc - local;
 }
 
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t P, uint32_t b2,
-                                              uint32_t* __restrict__ fine_off, uint32_t* __restrict__ cursor1,
-                                              uint32_t* __restrict__ cursor2, uint32_t* __restrict__ tile_off) {
+__global__ void __launch_bounds__(1024) k_scan_dist(const uint32_t* __restrict__ hist_all, uint32_t G, uint32_t rank,
+                                                   uint32_t P, uint32_t b2, unsigned long long capacity,
+                                                   uint32_t* __restrict__ fine_off, uint32_t* __restrict__ cursor1,
+                                                   uint32_t* __restrict__ cursor2, uint32_t* __restrict__ tile_off,
+                                                   unsigned long long* __restrict__ n_own, uint32_t* __restrict__ abort) {
     __shared__ uint32_t warp_sums[33];
-    __shared__ uint32_t s_l1[(1 << kMaxLevelBits) + 1];  // start offset of every level-1 bucket, then the total
-    const uint32_t per = (P + 1023u) / 1024u;
+    __shared__ unsigned long long s_bucket[kMaxPeers][1 << kMaxLevelBits];  // tuples rank src sends to level-1 bin B
+    __shared__ unsigned long long s_bstart[(1 << kMaxLevelBits)];           // start of bin B in its owner's buffer
+    __shared__ unsigned long long s_btot[(1 << kMaxLevelBits)];
+    __shared__ uint32_t s_abort;
+    const uint32_t P1 = P >> b2, PL = P / G, P1L = P1 / G;
+    for (uint32_t i = threadIdx.x; i < G * (1u << kMaxLevelBits); i += 1024u) (&s_bucket[0][0])[i] = 0ull;
+    if (threadIdx.x == 0) s_abort = *abort;  // the other relation of this join may already have overflowed
+    __syncthreads();
+    const uint32_t per = (P + 1023u) / 1024u;  // a power of two <= 2^b2 whenever P > 1024, else 1
     const uint32_t lo = threadIdx.x * per;
     uint32_t v[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; i++) v[i] = 0u;
+    const bool mine = lo < P && lo / PL == rank;
+    if (lo < P) {
+        for (uint32_t src = 0; src < G; src++) {
+            const uint32_t* row = hist_all + (size_t)src * P + lo;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < kBinsPerThread; i++) {
+                if ((uint32_t)i < per) {
+                    const uint32_t c = row[i];
+                    sum += c;
+                    if (mine) v[i] += c;
+                }
+            }
+            if (sum) atomicAdd(&s_bucket[src][lo >> b2], (unsigned long long)sum);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < P1) {
+        unsigned long long t = 0;
+        for (uint32_t src = 0; src < G; src++) t += s_bucket[src][threadIdx.x];
+        s_btot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {  // one thread per owner: exclusive scan over its <= 128 level-1 bins
+        unsigned long long run = 0;
+        for (uint32_t lb = 0; lb < P1L; lb++) {
+            s_bstart[threadIdx.x * P1L + lb] = run;
+            run += s_btot[threadIdx.x * P1L + lb];
+        }
+        if (run > capacity) {
+            *abort = 1u;
+            s_abort = 1u;
+        }
+        if (threadIdx.x == rank) *n_own = run;
+    }
+    __syncthreads();
+    // an overflow anywhere (every rank sees the same rows, so all ranks agree): the scatter kernels write nothing and the
+    // owned partitions are declared empty, so that nothing downstream reads past a buffer
+    const bool dead = s_abort != 0u;
+    if (dead && threadIdx.x == 0) *n_own = 0ull;
+    if (threadIdx.x < P1) {
+        unsigned long long before = 0;
+        for (uint32_t src = 0; src < rank; src++) before += s_bucket[src][threadIdx.x];
+        cursor1[threadIdx.x] = (uint32_t)(s_bstart[threadIdx.x] + before);
+    }
+    // fine offsets of the owned partitions (contiguous thread range: other threads contribute 0)
     uint32_t local = 0;
 #pragma unroll
     for (int i = 0; i < kBinsPerThread; i++) {
-        v[i] = ((uint32_t)i < per && lo + i < P) ? hist[lo + i] : 0u;
+        if (dead) v[i] = 0u;
         local += v[i];
     }
     uint32_t run = block_exclusive_scan_1024(local, warp_sums);
-    const uint32_t submask = (1u << b2) - 1u;
+    if (mine) {
+        const uint32_t pl = lo - rank * PL;
 #pragma unroll
-    for (int i = 0; i < kBinsPerThread; i++) {
-        const uint32_t p = lo + i;
-        if ((uint32_t)i < per && p < P) {
-            fine_off[p] = run;
-            cursor2[p] = run;
-            if ((p & submask) == 0u) {
-                cursor1[p >> b2] = run;
-                s_l1[p >> b2] = run;
+        for (int i = 0; i < kBinsPerThread; i++) {
+            if ((uint32_t)i < per && pl + i < PL) {
+                fine_off[pl + i] = run;
+                cursor2[pl + i] = run;
+                run += v[i];
             }
-            run += v[i];
         }
     }
-    const uint32_t P1 = P >> b2;
-    if (threadIdx.x == 0) {
-        const uint32_t total = warp_sums[32];
-        fine_off[P] = total;
-        s_l1[P1] = total;
-    }
+    if (threadIdx.x == 0) fine_off[PL] = warp_sums[32];
     __syncthreads();
-    // level-2 tile schedule: tiles per level-1 bucket (P1 <= 128), scanned by the same block scan
-    const uint32_t tiles =
-        threadIdx.x < P1 ? (s_l1[threadIdx.x + 1] - s_l1[threadIdx.x] + kScatterTile - 1) / kScatterTile : 0u;
+    // level-2 tile schedule over the owned level-1 bins, scanned by the same block scan
+    const uint32_t tiles = (threadIdx.x < P1L && !dead)
+                               ? (uint32_t)((s_btot[rank * P1L + threadIdx.x] + kScatterTile - 1) / kScatterTile)
+                               : 0u;
     const uint32_t tex = block_exclusive_scan_1024(tiles, warp_sums);
-    if (threadIdx.x <= P1) tile_off[threadIdx.x] = tex;  // thread P1 has tiles == 0: its prefix is the grand total
+    if (threadIdx.x <= P1L) tile_off[threadIdx.x] = tex;  // thread P1L has tiles == 0: its prefix is the grand total
 }
 
-// ---- destination-bin functions of the scatter kernel -----------------------------------------------------------------
-// MODE 1: radix level 1 (pid >> b2)      MODE 2: radix level 2 (pid & (2^b2-1))
-// MODE 3: hash bins ((crapwow(seed,key) & size_mask) >> oshift) & binmask -- owner GPU by filter slice, and level 1
-//         of the hash-partitioned join (partition = filter slice, so the filter can be built in shared memory)
-// MODE 4: owner GPU by hash slice, BLOCKED filter: (crc32c(seed,key) & nblocks_mask) >> oshift
-// MODE 5: MODE 3's bin function on the level-2 tile schedule (input = level-1 output)
-struct BinFn {
-    uint32_t pmask, b2, submask;            // radix modes
-    uint32_t seed, size_mask, oshift;       // hash modes
-    uint32_t binmask;                       // hash modes: mask applied after the shift (level 2), else ~0
+// ---- small peer-memory collectives (NVLink / NVSwitch, no host involvement) --------------------------------------------
+// Every rank maps the symmetric control blocks of its peers (CUDA IPC or peer access). All three kernels are stream
+// ordered like any other kernel and can be captured in a CUDA graph.
+struct PeerPtrs {
+    void* p[kMaxPeers];
 };
-template <int MODE>
-__device__ __forceinline__ uint32_t bin_of(const BinFn& f, const uint32_t* crc_tab, uint32_t key) {
-    if (MODE == 1) return (key & f.pmask) >> f.b2;
-    if (MODE == 2) return key & f.submask;
-    if (MODE == 3 || MODE == 5) return ((hash_crapwow(f.seed, key) & f.size_mask) >> f.oshift) & f.binmask;
-    return (crc32c_tab(crc_tab, f.seed, key) & f.size_mask) >> f.oshift;
-}
+constexpr uint32_t kFlagStride = 32;  // one 128-byte line per flag
 
-// histogram of owner bins (<= 128): per-warp shared counters, flushed with global atomics
-template <int MODE>
-__global__ void __launch_bounds__(256) k_owner_hist(const uint2* __restrict__ in, uint64_t n_static,
-                                                    const unsigned long long* __restrict__ n_ptr, BinFn f,
-                                                    const uint32_t* __restrict__ g_crc, uint32_t nbins,
-                                                    uint32_t* __restrict__ ghist) {
-    __shared__ uint32_t wh[8][1 << kMaxLevelBits];
-    __shared__ uint32_t crc_tab[MODE == 4 ? kCrcSmemWords : 1];
-    const uint64_t n = n_ptr ? (uint64_t)*n_ptr : n_static;
-    for (uint32_t i = threadIdx.x; i < 8 * nbins; i += blockDim.x) wh[i / nbins][i % nbins] = 0u;
-    if (MODE == 4) load_crc_tab(crc_tab, g_crc);
-    __syncthreads();
-    const uint32_t wid = threadIdx.x >> 5;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&wh[wid][bin_of<MODE>(f, crc_tab, in[i].x)], 1u);
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
-        uint32_t c = 0;
-        for (int w = 0; w < 8; w++) c += wh[w][b];
-        if (c) atomicAdd(&ghist[b], c);
+// all-gather of one row per rank: dst row `rank` on every peer <- src (words); used for the partition histograms and the
+// result words
+__global__ void k_push_rows(PeerPtrs dst, uint32_t world, uint32_t rank, const uint32_t* __restrict__ src, uint32_t words) {
+    for (uint32_t g = blockIdx.y; g < world; g += gridDim.y) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst.p[g]) + (size_t)rank * words;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) d[i] = src[i];
     }
 }
 
-// bitwise OR of a partial filter into the destination (multi-GPU general path: NCCL has no OR reduction)
+// barrier across the ranks: rank r publishes the next epoch in slot r of every peer's flag array (release, system scope;
+// everything earlier kernels of this stream stored -- locally or into peer memory -- is performed before it) and waits
+// until all slots of its own array have reached that epoch. The epoch lives on the device, so a replayed CUDA graph keeps
+// counting. A peer that never arrives trips the time-out instead of hanging the GPU.
+__global__ void k_barrier(PeerPtrs flags, uint32_t world, uint32_t rank, uint32_t* __restrict__ epoch,
+                          uint32_t* __restrict__ err, long long timeout_cycles) {
+    const uint32_t t = threadIdx.x;
+    const uint32_t e = *epoch + 1u;
+    __syncwarp();
+    if (t < world) {
+        __threadfence_system();
+        uint32_t* remote = reinterpret_cast<uint32_t*>(flags.p[t]) + rank * kFlagStride;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(e) : "memory");
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.p[rank]) + t * kFlagStride;
+        const long long t0 = clock64();
+        for (;;) {
+            uint32_t seen;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if ((int32_t)(seen - e) >= 0) break;
+            if (clock64() - t0 > timeout_cycles) {
+                *err = 2u;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    if (t == 0) *epoch = e;
+}
+
+// sum of the ranks' result rows (8 x u64 each, all-gathered by k_push_rows + barrier) -> out[8]; sums wrap mod 2^64
+__global__ void k_reduce_rows(const unsigned long long* __restrict__ rows, uint32_t world, unsigned long long* __restrict__ out) {
+    if (threadIdx.x < 8) {
+        unsigned long long s = 0;
+        for (uint32_t g = 0; g < world; g++) s += rows[g * 8 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
+// Non-sliceable filters (BASIC k > 1: a key's bits spread over the whole filter): every rank has inserted its local R into
+// a full-size partial filter; rank r ORs slice r of all partials (peer loads) and stores the result into slice r of every
+// rank's final filter (peer stores) -- reduce-scatter + all-gather of a bitwise OR, which NCCL has no operator for.
+__global__ void k_filter_or_bcast(PeerPtrs partials, PeerPtrs finals, uint32_t world, uint64_t first16, uint64_t n16) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t g = 0; g < world; g++) {
+            const uint4 b = reinterpret_cast<const uint4*>(partials.p[g])[first16 + i];
+            acc.x |= b.x; acc.y |= b.y; acc.z |= b.z; acc.w |= b.w;
+        }
+        for (uint32_t g = 0; g < world; g++) reinterpret_cast<uint4*>(finals.p[g])[first16 + i] = acc;
+    }
+}
+
+// bitwise OR of a partial filter into the destination (building block of the NCCL reference path)
 __global__ void k_filter_or(uint4* __restrict__ dst, const uint4* __restrict__ src, uint64_t n16) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
@@ -727,15 +722,18 @@ __global__ void k_filter_or(uint4* __restrict__ dst, const uint4* __restrict__ s
     }
 }
 
-// ---- K4: radix scatter with shared-memory staging ---------------------------------------------------------------
+// ---- K4: scatter with shared-memory staging ---------------------------------------------------------------------
 // replaces the scatter loop (:842-849) and pass-2 radix_cluster (:574-608).
 // Persistent CTAs; every CTA walks its tiles of kScatterTile tuples through a kScatterStages-deep ring of TMA
 // bulk loads (cp.async.bulk -> mbarrier), so the HBM read of the next tiles is in flight while the current tile
-// is sorted by destination bin in shared memory (per-warp histograms -> ranks), claims one contiguous range per
-// non-empty bin from the global cursors and writes every bin's run with coalesced stores.
-// LEVEL 1: input = whole relation, bin = pid >> b2, cursor index = bin.
-// LEVEL 2: input = level-1 output, work item = (bucket, tile) from tile_off, bin = pid & (2^b2-1),
-//          cursor index = pid.
+// is sorted by destination bin in shared memory (block-level shared atomics -> ranks), claims one contiguous range per
+// non-empty bin from the cursors and writes every bin's run with coalesced stores.
+// LEVEL 1: input = a whole relation (this rank's chunk), bin = pid >> b2 (a GLOBAL level-1 bin), cursor index = bin.
+//          PEER: the run goes to the receive buffer of the bin's owner GPU (peer memory over NVLink); the cursors were
+//          pre-computed from the all-gathered histograms (k_scan_dist), so the claim is a LOCAL atomic: the kernel is
+//          a fused partition + all-to-all with no remote atomics, no send buffers and no collective call.
+// LEVEL 2: input = the owned level-1 bins, work item = (bin, tile) from tile_off, bin = pid & (2^b2-1),
+//          cursor index = local pid.
 struct ScatterItem {
     uint64_t src_al;   // first tuple index of the bulk load (even: 16-byte aligned)
     uint32_t skip;     // 0/1 tuples to skip at the head of the staged tile
@@ -744,17 +742,17 @@ struct ScatterItem {
     uint32_t bytes;    // bulk-load size
 };
 
-template <int MODE>
+template <int LEVEL>
 __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ fine_off,
-                                                    const uint32_t* __restrict__ tile_off, uint32_t P1, uint32_t b2) {
+                                                    const uint32_t* __restrict__ tile_off, uint32_t P1L, uint32_t b2) {
     ScatterItem it;
     uint64_t src0;
-    if (MODE != 2 && MODE != 5) {
+    if (LEVEL == 1) {
         src0 = item * kScatterTile;
         it.cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
         it.cbase = 0u;
     } else {
-        uint32_t lo = 0, hi = P1;  // bucket j with tile_off[j] <= item < tile_off[j+1]
+        uint32_t lo = 0, hi = P1L;  // bin j with tile_off[j] <= item < tile_off[j+1]
         while (hi - lo > 1u) {
             uint32_t mid = (lo + hi) >> 1;
             if (tile_off[mid] <= (uint32_t)item) lo = mid; else hi = mid;
@@ -770,67 +768,44 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
     return it;
 }
 
-// REMOTE (multi-GPU, fused partition + all-to-all): bin g is owner GPU g; its run is claimed from GPU g's cursor with a
-// system-scope atomic over NVLink and stored straight into GPU g's receive buffer (peer memory), so the exchange
-// needs neither send buffers, counts on the host, nor a separate collective.
-struct PeerTargets {
-    uint2* buf[kMaxPeers];                  // receive buffers (peer device pointers mapped into this process)
-    unsigned long long* cursor[kMaxPeers];  // tuples received so far, lives on the owner
-    unsigned long long capacity;            // tuples per receive buffer
-    unsigned int* overflow;                 // local flag, set when a claim does not fit
+struct PeerBufs {
+    uint2* buf[kMaxPeers];  // receive buffers (peer device pointers mapped into this process; buf[rank] is local)
+    uint32_t shift;         // owner of level-1 bin B = B >> shift
 };
 
-// Pre-counted routing (experimental, HWBRJ_ROUTE_PRECOUNT=1): instead of one system-scope atomic per (tile, owner) on the
-// owners' cursors -- 8 GPUs x 7 800 tiles hammer the same 8 addresses over NVLink -- the sender counts its tuples per
-// owner first (k_owner_hist), claims its whole range on every owner with ONE remote atomic each, and the scatter kernel
-// sub-allocates from local cursors that start at the claimed bases.
-__global__ void k_route_claim(const uint32_t* __restrict__ counts, PeerTargets peers, uint32_t world,
-                              unsigned long long* __restrict__ local_cursor) {
-    const uint32_t b = threadIdx.x;
-    if (b >= world) return;
-    const unsigned long long tot = counts[b];
-    unsigned long long base = tot ? atomicAdd_system(peers.cursor[b], tot) : 0ull;
-    if (base + tot > peers.capacity) {  // does not fit: every later sub-claim lands beyond the capacity and is dropped
-        atomicExch(peers.overflow, 1u);
-        base = peers.capacity;
-    }
-    local_cursor[b] = base;
-}
-
-template <int MODE, bool REMOTE = false>
-__global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out,
-                                                            const uint64_t* __restrict__ n_ptr, uint64_t n_static,
-                                                            const uint32_t* __restrict__ fine_off,
-                                                            const uint32_t* __restrict__ tile_off,
-                                                            uint32_t* __restrict__ cursor, BinFn fn,
-                                                            const uint32_t* __restrict__ g_crc, uint32_t nbins,
-                                                            PeerTargets peers = PeerTargets()) {
+template <int LEVEL, int PMODE, bool PEER>
+__global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS)
+k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned long long* __restrict__ n_ptr,
+          uint64_t n_static, const uint32_t* __restrict__ fine_off, const uint32_t* __restrict__ tile_off,
+          uint32_t* __restrict__ cursor, PartFn pf, const uint32_t* __restrict__ g_crc, uint32_t nbins, uint32_t P1L,
+          PeerBufs peers, const uint32_t* __restrict__ abort_flag) {
     constexpr int PER = kScatterTile / kScatterThreads;
     constexpr int NB = 1 << kMaxLevelBits;
-    constexpr bool kKeepBin = MODE >= 3;  // hash owners: remember the bin; radix bins are recomputed from the key
+    constexpr bool kKeepBin = PMODE != 0;  // hash partitions: remember the bin; radix bins are recomputed from the key
     static_assert(kScatterThreads >= 32 + NB, "claims run on threads 32.. beside the scan warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* raw = reinterpret_cast<uint2*>(smem_raw);                       // [stages][kScatterStageTuples]
     uint2* sorted = raw + kScatterStages * kScatterStageTuples;            // [kScatterTile]
     __shared__ uint32_t hist[NB];       // tuples per bin of this tile (block-level shared atomics give the ranks)
     __shared__ uint32_t binstart[NB];   // exclusive scan of hist
-    __shared__ unsigned long long gclaim[REMOTE ? kMaxPeers : NB];
+    __shared__ uint32_t gclaim[NB];
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
     __shared__ uint8_t sorted_bin[kKeepBin ? kScatterTile : 1];
-    __shared__ uint32_t crc_tab[MODE == 4 ? kCrcSmemWords : 1];
-    const uint64_t n = n_ptr ? *n_ptr : n_static;
-    const uint32_t b2 = fn.b2;
-    const uint32_t P1 = (fn.pmask + 1u) >> b2;
-    const uint64_t nitems = (MODE != 2 && MODE != 5) ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1];
-    if (MODE == 4) load_crc_tab(crc_tab, g_crc);
+    __shared__ uint32_t crc_tab[PMODE == 2 ? kCrcSmemWords : 1];
+    if (abort_flag && *abort_flag) return;  // a receive buffer would overflow (k_scan_dist): nothing is written
+    const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;
+    const uint32_t b2 = pf.b2;
+    const uint32_t submask = (1u << b2) - 1u;
+    const uint64_t nitems = LEVEL == 1 ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1L];
+    if (PMODE == 2) load_crc_tab(crc_tab, g_crc);
     if (threadIdx.x == 0) {
         for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
         mbar_fence_init();
     }
     __syncthreads();
     auto issue = [&](uint64_t item, int st) {  // thread 0 only
-        ScatterItem it = scatter_item<MODE>(item, n, fine_off, tile_off, P1, b2);
+        ScatterItem it = scatter_item<LEVEL>(item, n, fine_off, tile_off, P1L, b2);
         desc[st] = it;
         mbar_arrive_expect_tx(&mbar[st], it.bytes);
         bulk_g2s(raw + st * kScatterStageTuples, in + it.src_al, it.bytes, &mbar[st]);
@@ -857,7 +832,8 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
                 t[j] = tile[idx];
-                uint32_t bin = bin_of<MODE>(fn, crc_tab, t[j].x);
+                const uint32_t pid = pid_of<PMODE>(pf, crc_tab, t[j].x);
+                const uint32_t bin = LEVEL == 1 ? pid >> b2 : pid & submask;
                 rank[j] = (bin << 24) | atomicAdd(&hist[bin], 1u);
             }
         }
@@ -890,16 +866,7 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
         } else if (threadIdx.x - 32u < nbins) {  // meanwhile: one output range per non-empty bin
             const uint32_t bb = threadIdx.x - 32u;
             const uint32_t tot = hist[bb];
-            if (REMOTE) {
-                unsigned long long c = tot ? atomicAdd_system(peers.cursor[bb], (unsigned long long)tot) : 0ull;
-                if (c + tot > peers.capacity) {  // does not fit: flag it and drop the run (the host falls back)
-                    atomicExch(peers.overflow, 1u);
-                    c = ~0ull;
-                }
-                gclaim[bb] = c;
-            } else {
-                gclaim[bb] = tot ? atomicAdd(&cursor[d.cbase + bb], tot) : 0u;
-            }
+            gclaim[bb] = tot ? atomicAdd(&cursor[d.cbase + bb], tot) : 0u;
         }
         __syncthreads();  // (C)
 #pragma unroll
@@ -915,13 +882,14 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
         __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
             const uint2 tt = sorted[i];
-            const uint32_t bin = kKeepBin ? (uint32_t)sorted_bin[i] : bin_of<MODE>(fn, crc_tab, tt.x);
-            if (REMOTE) {
-                unsigned long long c = gclaim[bin];
-                if (c != ~0ull) peers.buf[bin][c + (i - binstart[bin])] = tt;  // NVLink store (or local)
-            } else {
-                out[(uint32_t)gclaim[bin] + (i - binstart[bin])] = tt;
+            uint32_t bin;
+            if (kKeepBin) bin = (uint32_t)sorted_bin[i];
+            else {
+                const uint32_t pid = pid_of<PMODE>(pf, crc_tab, tt.x);
+                bin = LEVEL == 1 ? pid >> b2 : pid & submask;
             }
+            uint2* dst = (PEER && LEVEL == 1) ? peers.buf[bin >> peers.shift] : out;  // NVLink store when the owner is a peer
+            dst[gclaim[bin] + (i - binstart[bin])] = tt;
         }
         // next iteration: hist is rewritten before its first barrier, binstart/gclaim after (A'), sorted after (C'):
         // no thread can pass that first barrier before every thread has finished this write-out loop
@@ -929,21 +897,28 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS) k_sc
 }
 
 // ---- K1': Bloom filter built from hash partitions, in shared memory, without global atomics ------------------------
-// When the join partitions on the filter-slice index (partition p = keys whose bit lies in bits [p*S, (p+1)*S) of the
-// filter, S = m / 2^bits), every partition owns one contiguous slice: a CTA zeroes the slice in shared memory, ORs in
-// the bits of its partition's keys with shared-memory atomics and writes the slice out with coalesced stores. This
-// replaces add_generic's atomic OR per key (bloom_filter.c:74-89) for BASIC k = 1; the bitmap is byte-identical.
+// When the join partitions on the filter-slice index (PMODE 1/2), every partition owns one contiguous slice of
+// m / 2^bits bits: a CTA zeroes the slice in shared memory, ORs in the bits of its partition's keys with shared-memory
+// atomics and writes the slice out with coalesced stores. This replaces add_generic's atomic OR per key
+// (bloom_filter.c:74-89) for BASIC k <= 1 and for BLOCKED with any k (all k bits of a key lie in its block, and a slice is
+// a whole number of blocks); the bitmap is byte-identical. Every word of the filter is written, so no zero-fill is needed.
+// PEER: the slice is stored into the filter of EVERY rank (peer stores over NVLink): the slice build and the all-gather
+// that replicates the filter are one kernel.
+template <bool BLOCKED, bool PEER>
 __global__ void __launch_bounds__(512) k_filter_from_parts(const uint2* __restrict__ Rp, const uint32_t* __restrict__ r_off,
-                                                          uint32_t P, uint32_t* __restrict__ filter, uint32_t slice_words,
-                                                          uint32_t seed, uint32_t size_mask) {
-    extern __shared__ uint32_t s_slice[];  // two slices: a CTA alternates so that only one barrier separates partitions
+                                                          uint32_t PL, uint32_t gbase, uint32_t slice_words, BloomParams bp,
+                                                          const uint32_t* __restrict__ g_crc, PeerPtrs filters,
+                                                          uint32_t world, uint32_t nbuf) {
+    extern __shared__ uint32_t s_slice[];  // nbuf (1 or 2) slices: with 2 only one barrier separates partitions
+    __shared__ uint32_t crc_tab[BLOCKED ? kCrcSmemWords : 1];
     const uint32_t slice_mask = slice_words * 32u - 1u;
     const uint64_t pol = policy_evict_first();
     constexpr int U = 4;  // independent loads in flight per thread
-    for (uint32_t i = threadIdx.x; i < 2 * slice_words; i += blockDim.x) s_slice[i] = 0u;
+    if (BLOCKED) load_crc_tab(crc_tab, g_crc);
+    for (uint32_t i = threadIdx.x; i < nbuf * slice_words; i += blockDim.x) s_slice[i] = 0u;
     __syncthreads();
     uint32_t par = 0;
-    for (uint32_t p = blockIdx.x; p < P; p += gridDim.x, par ^= 1u) {
+    for (uint32_t p = blockIdx.x; p < PL; p += gridDim.x, par = nbuf == 2 ? par ^ 1u : 0u) {
         uint32_t* sl = s_slice + par * slice_words;
         const uint32_t lo = r_off[p], hi = r_off[p + 1];
         for (uint32_t i0 = lo + threadIdx.x; i0 < hi; i0 += U * blockDim.x) {
@@ -956,17 +931,30 @@ __global__ void __launch_bounds__(512) k_filter_from_parts(const uint2* __restri
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (i0 + u * blockDim.x < hi) {
-                    const uint32_t h = hash_crapwow(seed, key[u]) & size_mask & slice_mask;
-                    atomicOr(&sl[h >> 5], 1u << (h & 31u));
+                    uint32_t base, h, y;
+                    bp.blocked = BLOCKED ? 1u : 0u;
+                    bloom_start(bp, crc_tab, key[u], base, h, y);
+                    for (uint32_t i = 0; i < bp.k; i++) {  // the index sequence of add_generic, inside the slice
+                        const uint32_t a = (base + h) & slice_mask;
+                        atomicOr(&sl[a >> 5], 1u << (a & 31u));
+                        h = (h + y) & bp.size_mask;
+                        y = (y + i + 1u) & bp.size_mask;
+                    }
                 }
             }
         }
         __syncthreads();  // slice complete
-        uint32_t* dst = filter + (uint64_t)p * slice_words;
+        const size_t first = (size_t)(gbase + p) * slice_words;
         for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) {
-            dst[i] = sl[i];
-            sl[i] = 0u;  // ready for the partition after next; the next partition uses the other buffer meanwhile
+            const uint32_t w = sl[i];
+            if (PEER) {
+                for (uint32_t g = 0; g < world; g++) reinterpret_cast<uint32_t*>(filters.p[g])[first + i] = w;
+            } else {
+                reinterpret_cast<uint32_t*>(filters.p[0])[first + i] = w;
+            }
+            sl[i] = 0u;  // ready for a later partition; with two buffers the next partition uses the other one meanwhile
         }
+        if (nbuf != 2) __syncthreads();
     }
 }
 

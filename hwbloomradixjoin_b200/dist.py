@@ -1,5 +1,12 @@
-"""Multi-GPU Bloom-filter radix join: one process per GPU, torch.distributed (NCCL over NVLink /
-NVSwitch) for the exchange steps, the library's CUDA kernels for everything else.
+"""Multi-GPU Bloom-filter radix join, one process per GPU.
+
+Two implementations of the same sharding live here:
+  * DistGroup / DistJoinGraph (bottom of the file, the product path): the collective join runs inside the library
+    (hwbrj_dist_join): fused partition + all-to-all and fused filter-slice build + all-gather over NVLink peer memory,
+    device-side barriers; torch.distributed only carries the handles at start-up.
+  * dist_join (NCCL reference path): the same steps spelled out with torch.distributed all-to-all / all-gather /
+    all-reduce between the library's building-block kernels. It is what the peer-memory join is validated against, and
+    its orchestration is exercised on CPU with the gloo backend (tests/test_dist_gloo.py).
 
 Sharding. Rank g holds a contiguous chunk of R and of S (the GPU analogue of the reference's per-thread chunks,
 parallel_radix_join_bloom.c:1646-1672). Every key has one OWNER rank, a pure function of the key, so owners join
@@ -249,274 +256,116 @@ def dist_join(ops, Rshard: torch.Tensor, Sshard: torch.Tensor, bloom: Optional[B
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# NVLink peer-memory path: the exchanges are done BY the partitioning kernel (fused partition + all-to-all)
+# NVLink peer-memory path: the whole collective join runs below the C ABI (hwbrj_dist_*). torch.distributed is only the
+# launcher's channel for the 128-byte handles; the exchanges are peer-memory loads/stores issued by the library's own
+# kernels, ranks meet at device-side barriers, and nothing here touches the data.
 # ----------------------------------------------------------------------------------------------------------------
-class PeerFabric:
-    """Per-rank receive buffers that every peer of the NVLink domain can store into.
+class DistGroup:
+    """This rank's membership in a group of GPUs that join together (hwbrj_dist_t).
 
-    The buffers are allocated by the library (cudaMalloc) and exported as CUDA IPC handles; the 64-byte handles
-    travel through torch.distributed and each rank maps its peers' buffers. `hwbrj_route_peer` then writes every
-    tuple straight into its owner's buffer, claiming space from the owner's cursor with a system-scope atomic over
-    NVLink: no send buffers, no counts on the host, no collective for the data. Ranks are separated by tiny
-    stream-ordered all-reduces (route -> consume)."""
+    The library allocates one symmetric block per rank (receive buffers for the level-1 routing of R and of the filter
+    survivors, the replicated filter, gathered histogram / result rows, barrier flags) and exports a handle; the handles
+    travel through torch.distributed.all_gather and every rank maps its peers (CUDA IPC). `join` is then ONE call into
+    the library per rank."""
 
-    # two sets of control words {R cursor u64, S cursor u64, overflow u32, pad}: join i uses set i%2 and zeroes the other
-    # one, which no peer touches before join i+1 -- and every rank enters join i+1 only after the barriers of join i,
-    # i.e. after this rank's zeroing (stream order). So no extra "cursors are zero" barrier is needed.
-    CTRL_BYTES = 256
-    SET_BYTES = 32
-
-    def __init__(self, ops: "CudaOps", cap_r: int, cap_s: int, group=None):
+    def __init__(self, ops: "CudaOps", cap_r: int, cap_s: int, max_filter_bytes: int, group=None):
         self.ops, self.group = ops, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.cap_r, self.cap_s = int(cap_r), int(cap_s)
         L = ops.L
-        self.local = [L.hwbrj_symm_alloc((self.cap_r + 8) * 8), L.hwbrj_symm_alloc((self.cap_s + 8) * 8),
-                      L.hwbrj_symm_alloc(self.CTRL_BYTES)]
-        handles = torch.zeros(3 * N_IPC, dtype=torch.uint8)
-        ok = 1 if all(self.local) else 0  # a failed allocation is reported through the collective flag below as well
-        for i, p in enumerate(self.local):
-            buf = (C.c_ubyte * N_IPC)()
-            if not ok or L.hwbrj_ipc_export(p, buf) != 0:
-                ok = 0  # keep going: the failure is agreed on collectively below, nobody is left waiting
-            handles[i * N_IPC:(i + 1) * N_IPC] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
-        handles = handles.to(ops.device)
-        allh = [torch.empty_like(handles) for _ in range(self.world)]
-        dist.all_gather(allh, handles, group=group)
-        self.peer = []  # peer[g] = [recvR, recvS, ctrl] pointers valid in this process
-        for g in range(self.world):
-            if g == self.rank:
-                self.peer.append(list(self.local))
-                continue
-            hb = allh[g].cpu().numpy().tobytes()
-            ptrs = []
-            for i in range(3):
-                raw = (C.c_ubyte * N_IPC).from_buffer_copy(hb[i * N_IPC:(i + 1) * N_IPC])
-                p = L.hwbrj_ipc_open(raw) if ok else None
-                if not p:
-                    ok = 0
-                ptrs.append(p)
-            self.peer.append(ptrs)
-        # agree collectively: if any rank could not map a peer buffer, every rank gives up on the peer path together
+        buf = (C.c_ubyte * N.DIST_HANDLE_BYTES)()
+        self.h = L.hwbrj_dist_create(self.rank, self.world, int(cap_r), int(cap_s), int(max_filter_bytes), buf)
+        ok = 1 if self.h else 0  # a failed allocation is agreed on collectively below: nobody is left waiting
+        mine = torch.frombuffer(bytearray(buf), dtype=torch.uint8).to(ops.device)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=group)
+        blob = b"".join(t.cpu().numpy().tobytes() for t in allh)
+        if ok and L.hwbrj_dist_connect(self.h, blob) != 0:
+            ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=ops.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag.item()) == 0:
-            raise RuntimeError("CUDA IPC peer mapping unavailable on at least one rank")
-        self._bar = torch.zeros(1, dtype=torch.int32, device=ops.device)
-        self.ctrl_view = ops.view_int64(self.local[2], self.CTRL_BYTES // 8)
-        self.parity = 0
-        self.ctrl_view.zero_()
-        self.barrier()
+            if self.h:
+                L.hwbrj_dist_destroy(self.h)
+                self.h = None
+            raise RuntimeError("peer memory of the GPU group cannot be allocated or mapped on at least one rank")
 
-    def barrier(self):
-        """stream-ordered barrier across ranks (no host synchronisation)"""
-        dist.all_reduce(self._bar, group=self.group)
-
-    def ptr_array(self, which: int, byte_offset: int = 0):
-        arr = (C.c_void_p * self.world)()
-        for g in range(self.world):
-            arr[g] = self.peer[g][which] + byte_offset
-        return arr
-
-    def begin_join(self) -> int:
-        """switch to the other set of control words and zero the one the NEXT join will use; returns the byte offset
-        of the active set"""
-        self.parity ^= 1
-        nxt = (self.parity ^ 1) * (self.SET_BYTES // 8)
-        self.ctrl_view[nxt:nxt + self.SET_BYTES // 8].zero_()
-        return self.parity * self.SET_BYTES
-
-    def close(self):
-        L = self.ops.L
-        torch.cuda.synchronize()
-        self.barrier()
-        torch.cuda.synchronize()
-        for g in range(self.world):
-            if g != self.rank:
-                for p in self.peer[g]:
-                    L.hwbrj_ipc_close(p)
-        self.barrier()
-        torch.cuda.synchronize()
-        for p in self.local:
-            L.hwbrj_symm_free(p)
-
-
-N_IPC = 64  # HWBRJ_IPC_HANDLE_BYTES
-
-
-def dist_join_peer(ops: "CudaOps", fabric: PeerFabric, Rshard: torch.Tensor, Sshard: torch.Tensor,
-                   bloom: Optional[BloomFilterArgs], r_total: int, s_total: int, time_phases: bool = False) -> Optional[dict]:
-    """Collective join with the exchanges fused into the partitioning kernels (NVLink peer stores). Returns None when
-    a receive buffer overflowed (heavily skewed owners): the caller then uses dist_join (NCCL all-to-all)."""
-    if bloom is not None:
-        bloom.check()
-    group, world, rank = fabric.group, fabric.world, fabric.rank
-    L = ops.L
-    is_sliced = sliceable(bloom, world)
-    slice_args = bloom if is_sliced else None
-    cargs = slice_args.to_c() if slice_args is not None else None
-    cref = C.byref(cargs) if cargs is not None else None
-    tm = PhaseTimer(time_phases)
-    tm.mark("start")
-    coff = fabric.begin_join()
-    ctrl = fabric.local[2] + coff
-    # (1) R: fused partition + all-to-all
-    h = ops._wrap(Rshard)
-    rc = L.hwbrj_route_peer(h, world, cref, fabric.ptr_array(0), fabric.ptr_array(2, coff), fabric.cap_r, ctrl + 16)
-    L.hwbrj_rel_free(h)
-    if rc != 0:
-        raise RuntimeError("hwbrj_route_peer(R) failed")
-    fabric.barrier()
-    tm.mark("route_r_fused")
-    Rown = L.hwbrj_rel_wrap_counted(fabric.local[0], fabric.cap_r, ctrl, max(r_total // world, 1))
-    if os.environ.get("HWBRJ_DIST_OVERLAP_R") == "1" and L.hwbrj_join_prepare_r(Rown) < 0:  # experimental, see below
-        raise RuntimeError("hwbrj_join_prepare_r failed")
-    # (2) filter slice / partial + combine, (3) local pre-filter
-    if bloom is not None:
-        filt = torch.empty(max(bloom.m // 8, 16), dtype=torch.uint8, device=ops.device)
-        bc = bloom.to_c()
-        if L.hwbrj_filter_build(Rown, C.byref(bc), filt.data_ptr(), 1) != 0:
-            raise RuntimeError("hwbrj_filter_build failed")
-        tm.mark("filter_build")
-        filt = combine_filter(ops, filt, bloom, is_sliced, group)
-        tm.mark("filter_all_gather")
-        surv = ops.empty_tuples(Sshard.numel())
-        cnt = torch.zeros(1, dtype=torch.int64, device=ops.device)
-        hs = ops._wrap(Sshard)
-        if L.hwbrj_filter_probe_async(filt.data_ptr(), hs, C.byref(bc), surv.data_ptr(), cnt.data_ptr()) != 0:
-            raise RuntimeError("hwbrj_filter_probe_async failed")
-        L.hwbrj_rel_free(hs)
-        tm.mark("s_probe")
-        hsurv = L.hwbrj_rel_wrap_counted(surv.data_ptr(), surv.numel(), cnt.data_ptr(), surv.numel())
-    else:
-        cnt = None
-        hsurv = ops._wrap(Sshard)
-    # (4) survivors: fused partition + all-to-all
-    rc = L.hwbrj_route_peer(hsurv, world, cref, fabric.ptr_array(1), fabric.ptr_array(2, coff + 8), fabric.cap_s, ctrl + 16)
-    L.hwbrj_rel_free(hsurv)
-    if rc != 0:
-        raise RuntimeError("hwbrj_route_peer(S) failed")
-    fabric.barrier()
-    tm.mark("route_s_fused")
-    # (5) local join of owned R and owned survivors; counts stay on the device
-    Sown = L.hwbrj_rel_wrap_counted(fabric.local[1], fabric.cap_s, ctrl + 8, max(s_total // world, 1))
-    st = N.StatsT()
-    rc = L.hwbrj_join_device(Rown, Sown, None, C.byref(st))  # synchronises the stream to fetch the scalars
-    L.hwbrj_rel_free(Rown)
-    L.hwbrj_rel_free(Sown)
-    if rc != 0:
-        raise RuntimeError("hwbrj_join_device failed")
-    tm.mark("local_join")
-    c = fabric.ctrl_view[coff // 8:coff // 8 + 4].tolist()
-    filtered_local = int(cnt.item()) if cnt is not None else 0
-    overflow = c[2] & 0xFFFFFFFF
-    vals = _reduce_scalars([st.matches, filtered_local, st.checksum_pair, st.checksum_rpay, st.checksum_spay,
-                            st.checksum_key, overflow, c[0], c[1]], ops.device, group)
-    if vals[6]:
-        return None
-    out = {"matches": vals[0], "filtered": vals[1] if bloom is not None else -1, "checksum_pair": vals[2],
-           "checksum_rpay": vals[3], "checksum_spay": vals[4], "checksum_key": vals[5], "sliced_filter": is_sliced,
-           "world": world, "r_owned_total": vals[7], "s_owned_total": vals[8], "local": st.as_dict(),
-           "path": "nvlink-peer-stores"}
-    if tm.enabled:
-        torch.cuda.synchronize()
-        out["phases_ms"] = tm.phases_ms()
-    return out
-
-
-# ----------------------------------------------------------------------------------------------------------------
-# The same pipeline as ONE CUDA graph: kernels, NVLink peer stores, barriers, filter all-gather and the final
-# all-reduce are captured once and replayed per join, so there is no launch gap between the ~20 short kernels.
-# ----------------------------------------------------------------------------------------------------------------
-def _peer_pipeline_async(ops: "CudaOps", fabric: PeerFabric, Rshard, Sshard, bloom, r_total, s_total, keep):
-    """dist_join_peer without any host synchronisation: returns the all-reduced int64 vector (device)
-    [matches, filtered, cpair, crpay, cspay, ckey, overflow, r_owned, s_owned]. `keep` collects the tensors that
-    must stay alive as long as the captured graph."""
-    group, world = fabric.group, fabric.world
-    L = ops.L
-    L.hwbrj_set_stream(torch.cuda.current_stream(ops.device).cuda_stream)
-    is_sliced = sliceable(bloom, world)
-    slice_args = bloom if is_sliced else None
-    cargs = slice_args.to_c() if slice_args is not None else None
-    cref = C.byref(cargs) if cargs is not None else None
-    ctrl = fabric.local[2]  # set 0 only: the graph starts with an explicit reset + barrier
-    fabric.ctrl_view[0:4].zero_()
-    fabric.barrier()
-    h = ops._wrap(Rshard)
-    if L.hwbrj_route_peer(h, world, cref, fabric.ptr_array(0), fabric.ptr_array(2, 0), fabric.cap_r, ctrl + 16) != 0:
-        raise RuntimeError("hwbrj_route_peer(R) failed")
-    L.hwbrj_rel_free(h)
-    fabric.barrier()
-    Rown = L.hwbrj_rel_wrap_counted(fabric.local[0], fabric.cap_r, ctrl, max(r_total // world, 1))
-    cnt = torch.zeros(1, dtype=torch.int64, device=ops.device)
-    keep.append(cnt)
-    if os.environ.get("HWBRJ_DIST_OVERLAP_R") == "1":
-        # experimental: the owned R is partitioned on the library's side stream while this stream builds, gathers and
-        # probes the filter; the local join at the end picks the partitions up (hwbrj_join_prepare_r)
-        if L.hwbrj_join_prepare_r(Rown) < 0:
-            raise RuntimeError("hwbrj_join_prepare_r failed")
-    if bloom is not None:
-        filt = torch.empty(max(bloom.m // 8, 16), dtype=torch.uint8, device=ops.device)
-        bc = bloom.to_c()
-        if L.hwbrj_filter_build(Rown, C.byref(bc), filt.data_ptr(), 1) != 0:
-            raise RuntimeError("hwbrj_filter_build failed")
-        filt = combine_filter(ops, filt, bloom, is_sliced, group)
-        surv = ops.empty_tuples(Sshard.numel())
-        keep += [filt, surv]
-        hs = ops._wrap(Sshard)
-        if L.hwbrj_filter_probe_async(filt.data_ptr(), hs, C.byref(bc), surv.data_ptr(), cnt.data_ptr()) != 0:
-            raise RuntimeError("hwbrj_filter_probe_async failed")
-        L.hwbrj_rel_free(hs)
-        hsurv = L.hwbrj_rel_wrap_counted(surv.data_ptr(), surv.numel(), cnt.data_ptr(), surv.numel())
-    else:
-        hsurv = ops._wrap(Sshard)
-    if L.hwbrj_route_peer(hsurv, world, cref, fabric.ptr_array(1), fabric.ptr_array(2, 8), fabric.cap_s, ctrl + 16) != 0:
-        raise RuntimeError("hwbrj_route_peer(S) failed")
-    L.hwbrj_rel_free(hsurv)
-    fabric.barrier()
-    Sown = L.hwbrj_rel_wrap_counted(fabric.local[1], fabric.cap_s, ctrl + 8, max(s_total // world, 1))
-    out6 = torch.zeros(8, dtype=torch.int64, device=ops.device)
-    keep.append(out6)
-    launches = L.hwbrj_join_device_async(Rown, Sown, None, out6.data_ptr())
-    L.hwbrj_rel_free(Rown)
-    L.hwbrj_rel_free(Sown)
-    if launches < 0:
-        raise RuntimeError("hwbrj_join_device_async failed")
-    cv = fabric.ctrl_view
-    vec = torch.stack([out6[0], cnt[0], out6[1], out6[2], out6[3], out6[4], cv[2] & 0xFFFFFFFF, cv[0], cv[1]])
-    dist.all_reduce(vec, group=group)  # int64 lanes wrap modulo 2^64 exactly like the uint64 sums they carry
-    keep.append(vec)
-    return vec, is_sliced, launches
-
-
-class PeerJoinGraph:
-    """dist_join_peer captured as a CUDA graph for fixed shard tensors; replay() runs one join and returns the global
-    scalars (or None on receive-buffer overflow)."""
-
-    def __init__(self, ops: "CudaOps", fabric: PeerFabric, Rshard, Sshard, bloom, r_total, s_total):
+    def join(self, Rshard: torch.Tensor, Sshard: torch.Tensor, bloom: Optional[BloomFilterArgs], r_total: int) -> Optional[dict]:
+        """Collective join of the ranks' chunks; the scalars are global and identical on every rank. Returns None when
+        a receive buffer was too small (heavily skewed owners) or a peer did not arrive."""
         if bloom is not None:
             bloom.check()
-        self.ops, self.bloom, self.keep = ops, bloom, [Rshard, Sshard]
+        L = self.ops.L
+        L.hwbrj_set_stream(torch.cuda.current_stream(self.ops.device).cuda_stream)
+        hr, hs = self.ops._wrap(Rshard), self.ops._wrap(Sshard)
+        cargs = bloom.to_c() if bloom is not None else None
+        st = N.StatsT()
+        rc = L.hwbrj_dist_join(self.h, hr, hs, C.byref(cargs) if cargs is not None else None, int(r_total), C.byref(st))
+        L.hwbrj_rel_free(hr)
+        L.hwbrj_rel_free(hs)
+        if rc == -2:
+            return None
+        if rc != 0:
+            raise RuntimeError(f"hwbrj_dist_join rc={rc}")
+        d = st.as_dict()
+        return {"matches": d["matches"], "filtered": d["filtered"], "checksum_pair": d["checksum_pair"],
+                "checksum_rpay": d["checksum_rpay"], "checksum_spay": d["checksum_spay"], "checksum_key": d["checksum_key"],
+                "world": self.world, "owned_r": d["owned_r"], "owned_s": d["owned_s"], "local": d,
+                "path": "nvlink-peer-memory (in-library)"}
+
+    def filter_bytes(self, nbytes: int) -> bytes:
+        """this rank's copy of the replicated filter (tests: it must be byte-identical on every rank)"""
+        ptr = self.ops.L.hwbrj_dist_filter(self.h)
+        return self.ops.view_int64(ptr, nbytes // 8).cpu().numpy().tobytes()
+
+    def close(self):
+        if self.h:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody unmaps memory a peer may still write to
+            self.ops.L.hwbrj_dist_destroy(self.h)
+            self.h = None
+            dist.barrier(group=self.group)
+
+
+class DistJoinGraph:
+    """DistGroup.join captured as ONE CUDA graph for fixed chunk tensors (kernels, NVLink stores and device-side barriers;
+    no host work between them); replay() runs one join and returns the global scalars (None on overflow / time-out)."""
+
+    def __init__(self, grp: DistGroup, Rshard: torch.Tensor, Sshard: torch.Tensor, bloom: Optional[BloomFilterArgs], r_total: int):
+        if bloom is not None:
+            bloom.check()
+        self.grp, self.bloom = grp, bloom
+        self.keep = [Rshard, Sshard]
+        ops, L = grp.ops, grp.ops.L
+        self.out8 = torch.zeros(8, dtype=torch.int64, device=ops.device)
+        cargs = bloom.to_c() if bloom is not None else None
+        cref = C.byref(cargs) if cargs is not None else None
+        hr, hs = ops._wrap(Rshard), ops._wrap(Sshard)
+
+        def enqueue():
+            L.hwbrj_set_stream(torch.cuda.current_stream(ops.device).cuda_stream)
+            n = L.hwbrj_dist_join_async(grp.h, hr, hs, cref, int(r_total), self.out8.data_ptr())
+            if n < 0:
+                raise RuntimeError("hwbrj_dist_join_async failed")
+            return n
         side = torch.cuda.Stream(device=ops.device)
         side.wait_stream(torch.cuda.current_stream(ops.device))
-        with torch.cuda.stream(side):  # warm-up on a side stream: allocations, attributes, NCCL connections
+        with torch.cuda.stream(side):  # warm-up on a side stream: workspace allocations happen here, not during capture
             for _ in range(2):
-                _peer_pipeline_async(ops, fabric, Rshard, Sshard, bloom, r_total, s_total, [])
+                enqueue()
         torch.cuda.current_stream(ops.device).wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.vec, self.is_sliced, self.launches = _peer_pipeline_async(ops, fabric, Rshard, Sshard, bloom, r_total,
-                                                                           s_total, self.keep)
-        ops.L.hwbrj_set_stream(torch.cuda.current_stream(ops.device).cuda_stream)
-        self.world = fabric.world
+            self.launches = enqueue()
+        L.hwbrj_set_stream(torch.cuda.current_stream(ops.device).cuda_stream)
+        L.hwbrj_rel_free(hr)
+        L.hwbrj_rel_free(hs)
 
     def replay(self) -> Optional[dict]:
         self.graph.replay()
-        v = [x & MASK64 for x in self.vec.tolist()]  # the only host synchronisation of the join
+        v = [x & MASK64 for x in self.out8.tolist()]  # the only host synchronisation of the join
         if v[6]:
             return None
-        return {"matches": v[0], "filtered": v[1] if self.bloom is not None else -1, "checksum_pair": v[2],
-                "checksum_rpay": v[3], "checksum_spay": v[4], "checksum_key": v[5], "sliced_filter": self.is_sliced,
-                "world": self.world, "r_owned_total": v[7], "s_owned_total": v[8], "path": "nvlink-peer-stores+cuda-graph",
-                "local": {"kernel_launches": self.launches}}
+        return {"matches": v[0], "filtered": v[5] if self.bloom is not None else -1, "checksum_pair": v[1],
+                "checksum_rpay": v[2], "checksum_spay": v[3], "checksum_key": v[4], "world": self.grp.world,
+                "path": "nvlink-peer-memory (in-library) + cuda-graph", "local": {"kernel_launches": self.launches}}

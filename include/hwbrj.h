@@ -127,8 +127,10 @@ typedef struct hwbrj_stats_t {
     int32_t  radix_bits;      /* total radix bits used */
     int32_t  range_passes;    /* filter range passes used by insert/probe */
     int32_t  n_gpus;
-    float    ms_comm;         /* multi-GPU: time in collectives */
+    float    ms_comm;         /* reserved */
     float    reserved[3];
+    uint64_t owned_r;         /* R tuples this GPU owns after the routing (host-buffer multi-GPU calls: the maximum) */
+    uint64_t owned_s;         /* probe tuples (filter survivors) this GPU owns: the per-GPU load of the join phase */
 } hwbrj_stats_t;
 
 /* results of the most recent join in this process */
@@ -139,14 +141,22 @@ uint64_t hwbrj_last_checksum(void); /* checksum_pair */
 int      hwbrj_last_filter(unsigned char * bitmap_out, uint64_t nbytes);
 
 void hwbrj_set_quiet(int quiet);    /* 1: suppress the reference-style stdout lines */
-/* tuning knobs (also read from env HWBRJ_RADIX_BITS / HWBRJ_RANGE_PASSES); 0 = automatic */
+/* tuning knobs (also read from env HWBRJ_RADIX_BITS / HWBRJ_NUM_PASSES / HWBRJ_RANGE_PASSES); 0 = automatic.
+ * radix_bits and num_passes are the runtime form of the reference's compile-time NUM_RADIX_BITS / NUM_PASSES
+ * (prj_params.h:15-22, swept by measurements/run.py:205-269): total partition bits (<= 14) and 1 or 2 scatter passes
+ * (one pass handles at most 7 bits; more bits always take two). */
 void hwbrj_set_radix_bits(int bits);
+void hwbrj_set_num_passes(int passes);
 void hwbrj_set_range_passes(int passes);
+/* Host-buffer entry points (BPRO, PRO, ...): shard the relations over the first n GPUs of this process (contiguous
+ * chunks, like the reference's worker threads, parallel_radix_join_bloom.c:1646-1672) and join them together over
+ * NVLink peer memory. n must be a power of two <= the device count; the GPUs need peer access. Returns 0 on success. */
+int  hwbrj_set_gpus(int n);
 /* host-buffer Bloom joins: upload S in chunks on a copy stream and probe each chunk as it lands (hides the join
  * under the PCIe copy; TOTAL-TIME-USECS then includes waiting for the copies). Off by default. */
 void hwbrj_set_overlap_h2d(int on);
-/* partition the join on the filter-slice index and build the filter in shared memory (BASIC k<=1):
- * 0 never, 1 when the filter exceeds 32 MiB (default), 2 whenever the slices fit */
+/* partition the join on the filter-slice index and build the filter in shared memory (BASIC k<=1, BLOCKED any k):
+ * 0 never, 1 when the filter exceeds 32 MiB or several GPUs join (default), 2 whenever the slices fit */
 void hwbrj_set_hash_partition(int mode);
 const char * hwbrj_version(void);
 int  hwbrj_device_count(void);
@@ -174,16 +184,10 @@ void     hwbrj_rel_free(hwbrj_rel_t * rel);
 int hwbrj_join_device(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
                       hwbrj_stats_t * out);
 
-/* enqueue-only variant (no events, no host synchronisation: can be captured in a CUDA graph together with the
- * collectives around it). Leaves {matches, checksum_pair, checksum_rpay, checksum_spay, checksum_key, filtered}
- * as six uint64 in d_out6 (device). Returns the number of kernels enqueued, < 0 on error. */
-int hwbrj_join_device_async(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args, void * d_out6);
-/* Partition the build side of a FILTER-LESS join ahead of time: the histogram and scatter passes of R (the R half of
- * :808-849) are enqueued on a library-owned side stream forked from the current stream, so that they overlap whatever the
- * caller enqueues next (the multi-GPU join: filter all-gather and S probe). The next hwbrj_join_device[_async](R, S, NULL)
- * on the same relation joins the side stream and skips those passes. Returns the number of kernel launches, < 0 on
- * error. Experimental (HWBRJ_DIST_OVERLAP_R=1 in hwbloomradixjoin_b200.dist). */
-int hwbrj_join_prepare_r(const hwbrj_rel_t * R);
+/* enqueue-only variant (no events, no host synchronisation: can be captured in a CUDA graph). Leaves {matches,
+ * checksum_pair, checksum_rpay, checksum_spay, checksum_key, filtered, error flags, 0} as eight uint64 in d_out8 (device).
+ * Returns the number of kernels enqueued, < 0 on error. */
+int hwbrj_join_device_async(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args, void * d_out8);
 
 /* pinned host buffers for callers that want full-speed PCIe copies (bench e2e leg) */
 void * hwbrj_host_alloc(uint64_t bytes);
@@ -212,46 +216,58 @@ int64_t hwbrj_fpr_count(const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloo
  * partition boundaries (parallel_radix_join_bloom.c:574-608,759-852 equivalent) */
 int hwbrj_radix_partition(const tuple_t * in, uint64_t n, int bits, tuple_t * out, uint64_t * offsets);
 
-/* ---- multi-GPU building blocks ------------------------------------------------------------
- * One process per GPU; the host side (hwbloomradixjoin_b200/dist.py) runs these between torch.distributed / NCCL
- * collectives. All take device pointers and run on the stream given to hwbrj_set_stream(). */
+/* ---- the multi-GPU join: one rank per GPU -------------------------------------------------------------
+ * The join shards on the HIGH bits of the partition id: rank g owns partitions [g*P/G, (g+1)*P/G) -- for a BASIC (k <= 1)
+ * or BLOCKED filter these are the keys whose filter bits lie in the g-th 1/G slice of the filter. Per rank and join:
+ *   histogram of the local R chunk -> rows all-gathered over NVLink -> every rank derives where its tuples go ->
+ *   level-1 scatter stores straight into the owners' receive buffers (fused partition + all-to-all, no remote atomics) ->
+ *   level-2 scatter + filter-slice build in shared memory, each slice stored into EVERY rank's filter (fused build +
+ *   all-gather) -> probe of the local S chunk against the replicated filter -> only the survivors are routed the same
+ *   way -> per-partition build + probe on the owner -> result words all-gathered and summed.
+ * All exchanges are peer-memory loads/stores issued by the kernels themselves; ranks meet at device-side barriers.
+ * A rank is a process with one GPU (handles travel through the launcher's channel, e.g. torch.distributed.all_gather or
+ * MPI) or one of several GPUs driven by one process (hwbrj_set_gpus does all of this internally). */
+typedef struct hwbrj_dist hwbrj_dist_t;
+#define HWBRJ_DIST_HANDLE_BYTES 128
+/* allocate this rank's symmetric block on the CURRENT device: receive buffers of cap_r / cap_s tuples and room for a filter
+ * of max_filter_bytes; writes the handle peers need (HWBRJ_DIST_HANDLE_BYTES) to handle_out. world: power of two <= 16. */
+hwbrj_dist_t * hwbrj_dist_create(int rank, int world, uint64_t cap_r, uint64_t cap_s, uint64_t max_filter_bytes,
+                                 void * handle_out);
+/* map the peers; all_handles = the world handles in rank order. Returns 0 on success. */
+int  hwbrj_dist_connect(hwbrj_dist_t * d, const void * all_handles);
+/* collective: every rank calls it with its chunks of R and S. r_total = |R| over all ranks. The scalars of `out`
+ * (matches, filtered, checksums) are the global ones, identical on every rank; timings are this rank's.
+ * Returns 0, -2 if a receive buffer was too small or a peer did not arrive (results invalid). */
+int  hwbrj_dist_join(hwbrj_dist_t * d, const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
+                     uint64_t r_total, hwbrj_stats_t * out);
+/* enqueue-only variant on the stream of hwbrj_set_stream() (capturable in a CUDA graph): d_out8 as in
+ * hwbrj_join_device_async, already summed over the ranks */
+int  hwbrj_dist_join_async(hwbrj_dist_t * d, const hwbrj_rel_t * R, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
+                           uint64_t r_total, void * d_out8);
+void * hwbrj_dist_filter(hwbrj_dist_t * d); /* this rank's copy of the replicated filter (device pointer) */
+void hwbrj_dist_destroy(hwbrj_dist_t * d);
+
+/* ---- plumbing shared by the multi-GPU paths ---------------------------------------------------------------------- */
 void hwbrj_set_stream(void * cuda_stream); /* run on the caller's stream (0 = the legacy default stream) */
 void hwbrj_reset_stream(void);             /* back to the library's own stream */
 int  hwbrj_sync(void);
-int  hwbrj_set_device(int device);           /* before the first call: one process per GPU */
+int  hwbrj_set_device(int device);           /* cudaSetDevice: the current device selects the library's context */
 /* non-owning view of device memory; the pointer must be 16-byte aligned (NULL otherwise); an odd tuple count makes the
  * kernels read (not use) 8 bytes past the last tuple, which stay inside the allocation's last page */
 hwbrj_rel_t * hwbrj_rel_wrap(void * device_tuples, uint64_t n);
-/* same, but the real tuple count is a device-resident uint64 (written by an earlier kernel): `capacity` bounds it,
- * `expected` sizes the radix fan-out. Lets a pipeline run without host round trips. */
-hwbrj_rel_t * hwbrj_rel_wrap_counted(void * device_tuples, uint64_t capacity, const void * d_count, uint64_t expected);
 void *        hwbrj_rel_ptr(const hwbrj_rel_t * rel);
 /* positions [begin, begin+count) of the global generated relation (a rank's contiguous input chunk, the GPU
  * analogue of the per-thread chunks of parallel_radix_join_bloom.c:1646-1672) */
 hwbrj_rel_t * hwbrj_rel_generate_shard(int kind, uint64_t n, uint64_t r, double q, uint64_t seed, uint64_t begin,
                                        uint64_t count);
+
+/* ---- building blocks of the NCCL reference path (hwbloomradixjoin_b200/dist.py: dist_join), which exchanges with
+ * torch.distributed all-to-all / all-gather and is what the peer-memory join above is validated against ------------- */
 /* group the tuples by owner GPU into d_out (n tuples) and return the per-owner counts (host array of `world`).
  * Owner = the GPU holding the filter slice of the key's first bit (slice_args BASIC k<=1 or BLOCKED), else the
  * top bits of crapwow(42,key); equal keys always share an owner, so owners join independently. */
 int hwbrj_owner_partition(const hwbrj_rel_t * in, int world, const bloom_filter_args_t * slice_args, void * d_out,
                           uint64_t * counts_out);
-/* peer memory: buffers other ranks of the NVLink domain write into. The 64-byte handles travel through the host's
- * own channel (e.g. torch.distributed.all_gather) and are opened by every peer. */
-#define HWBRJ_IPC_HANDLE_BYTES 64
-void * hwbrj_symm_alloc(uint64_t bytes); /* zero-initialised device memory that can be exported */
-void   hwbrj_symm_free(void * p);
-int    hwbrj_ipc_export(void * p, void * handle_out /* HWBRJ_IPC_HANDLE_BYTES */);
-void * hwbrj_ipc_open(const void * handle);
-int    hwbrj_ipc_close(void * p);
-/* fused partition-by-owner + all-to-all: every tuple of `in` is stored straight into its owner's receive buffer
- * (peer_bufs[g], capacity_tuples each) at a position claimed from the owner's cursor (peer_cursors[g], uint64) with
- * a system-scope atomic over NVLink. A claim that does not fit sets *d_overflow_flag (uint32) and is dropped.
- * The caller separates routing from consumption with a stream-ordered barrier across ranks. */
-int hwbrj_route_peer(const hwbrj_rel_t * in, int world, const bloom_filter_args_t * slice_args, void * const * peer_bufs,
-                     void * const * peer_cursors, uint64_t capacity_tuples, void * d_overflow_flag);
-/* hwbrj_filter_probe without the host round trip: the survivor count is left in *d_count_out (device uint64) */
-int hwbrj_filter_probe_async(const void * d_filter, const hwbrj_rel_t * S, const bloom_filter_args_t * args,
-                             void * d_out, void * d_count_out);
 /* insert R's keys into the full-size filter at d_filter (m/8 bytes, device) */
 int hwbrj_filter_build(const hwbrj_rel_t * R, const bloom_filter_args_t * args, void * d_filter, int zero_first);
 /* dst |= src over nbytes (multiple of 16): combines partial filters (NCCL has no bitwise-OR reduction) */

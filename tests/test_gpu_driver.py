@@ -52,3 +52,40 @@ def test_driver_rejects_bad_arguments(Hgpu):
     assert p.returncode != 0 and "m must be a power of 2" in p.stdout
     p = subprocess.run([exe, "-a", "NOPE"], capture_output=True, text=True)
     assert "does not exist" in p.stdout
+
+
+def _golden():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "driver_golden.json")))
+
+
+@pytest.mark.parametrize("case", _golden(), ids=lambda c: c["args"].replace(" ", ""))
+def test_driver_matches_the_reference_binary_on_seeded_generators(Hgpu, case):
+    """--non-unique, --full-range and -z inputs depend on glibc rand() and the seeds: the same command line must print
+    what the UNMODIFIED reference binary printed (tests/golden/driver_golden.json)"""
+    out = run(case["args"].split())
+    assert f"Results = {case['results']}." in out
+    if case["filtered"] is not None and " RJ " not in f" {case['args']} ":
+        assert f"S-tuples after filter: {case['filtered']}" in out
+
+
+def test_driver_loads_relations_from_files(Hgpu, tmp_path):
+    """-R / -S (load_relation, generator.c:418-436,686-741): dump seeded inputs, load them back, same result"""
+    prefix = str(tmp_path / "rel_")
+    gen = "-r 120000 -s 600000 -q 0.3 --non-unique -x 5 -y 6".split()
+    run(gen + ["--dump-relations", prefix])
+    direct = run(gen + "-b basic -m 1048576 -k 1".split())
+    loaded = run(["-r", "120000", "-s", "600000", "-R", prefix + "R.tbl", "-S", prefix + "S.tbl"] + "-b basic -m 1048576 -k 1".split())
+    pick = lambda o: (re.search(r"Results = (\d+)", o).group(1), re.search(r"after filter: (\d+)", o).group(1))
+    assert pick(direct) == pick(loaded)
+    assert "Loading relation R" in loaded
+
+
+def test_driver_on_several_gpus(Hgpu):
+    if Hgpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    one = run("-a PRO -r 250000 -s 2000000 -q 0.01 -b basic -m 2097152 -k 1".split())
+    two = run("-a PRO -r 250000 -s 2000000 -q 0.01 -b basic -m 2097152 -k 1 --gpus 2".split())
+    assert "S-tuples after filter: 241986" in one and "S-tuples after filter: 241986" in two
+    assert "Results = 20000." in two
+    assert re.search(r"H2D-COPY-USECS, END-TO-END-USECS, GPUS: \n[\d.]+ \t [\d.]+\t 2 ", two)
