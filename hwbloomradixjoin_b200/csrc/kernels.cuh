@@ -405,7 +405,7 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
     }
 }
 
-// ---- K2 for k >= 2, staged (HWBRJ_PROBE_STAGED=1; parity-checked on hardware in round 2, tests/test_gpu_parity.py) ----
+// ---- K2 for k >= 2, staged (default for k >= 2; HWBRJ_PROBE_STAGED=0 selects k_probe_compact; both parity-checked) ----
 // With several probes per key the plain kernel walks probes 2..k under divergence: after the first probe 38 % of the
 // lanes are still alive at C1-blocked (k = 4), then 14 %, then 5 %, but the warp pays for every round. Here the keys that
 // pass their FIRST probe are compacted into a per-warp candidate ring (the tuple only), and probes 2..k run on full

@@ -49,8 +49,13 @@ def _run(env_extra):
 
 
 def test_staged_probe_matches_oracle():
-    """k_probe_staged (HWBRJ_PROBE_STAGED=1): probes 2..k on compacted candidates; BLOCKED and BASIC, ranged and not"""
+    """k_probe_staged (the default for k >= 2): probes 2..k on compacted candidates; BLOCKED and BASIC, ranged and not"""
     assert _run({"HWBRJ_PROBE_STAGED": "1"}) == []
+
+
+def test_unstaged_probe_matches_oracle():
+    """HWBRJ_PROBE_STAGED=0: all k probes of a key inside k_probe_compact"""
+    assert _run({"HWBRJ_PROBE_STAGED": "0"}) == []
 
 
 def test_staged_probe_with_forced_range_passes():
