@@ -116,6 +116,11 @@ struct Ctx {
     uint64_t zipf_r = 0;
     double zipf_theta = -1.0;
     int occ_scatter = 1, occ_join = 1, occ_probe[8] = {0}, occ_staged = 1;
+    // HWBRJ_TRACE=1: one CUDA event after every launch of a (non-captured) join; the per-kernel times are printed to stderr
+    bool trace = false;
+    std::vector<cudaEvent_t> tr_ev;
+    std::vector<const char*> tr_name;
+    size_t tr_n = 0;
 };
 
 static Ctx g_ctx[kMaxPeers];  // one context per device of this process (one process per GPU uses exactly one)
@@ -182,6 +187,7 @@ static void init_ctx() {
     if (const char* s = getenv("HWBRJ_PROBE_CARVEOUT")) g.probe_carveout = std::min(100, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_STAGED")) g.probe_staged = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_HASH_PARTITION")) g.hash_partition = std::max(0, std::min(2, atoi(s)));
+    if (const char* s = getenv("HWBRJ_TRACE")) g.trace = atoi(s) != 0;
     // kernel attributes are per device: every instantiation the pipeline can launch is prepared here
     set_smem(k_build_hist<false, 0>, kHistSmem); set_smem(k_build_hist<false, 1>, kHistSmem);
     set_smem(k_build_hist<false, 2>, kHistSmem); set_smem(k_build_hist<true, 0>, kHistSmem);
@@ -292,8 +298,32 @@ static int pick_b2(int bits, int gbits) {
     if (passes <= 0) passes = bits > kMaxLevelBits ? 2 : 1;
     if (passes == 1 || bits < 2) return 0;
     int b2 = std::min(bits / 2, bits - gbits);  // the owner is a prefix of the level-1 bin
+    if (const char* s = getenv("HWBRJ_L1_BITS")) b2 = bits - std::max(gbits, std::min(atoi(s), bits));  // experiments
     if (bits - b2 > kMaxLevelBits) b2 = bits - kMaxLevelBits;
+    if (b2 > kMaxLevelBits) b2 = kMaxLevelBits;  // (then the fan-out shrinks: bits are capped by the caller's override)
     return std::max(b2, 0);
+}
+
+// ---- per-launch trace (HWBRJ_TRACE=1) ------------------------------------------------------------------------------
+static bool g_tracing = false;  // set by run_join for the duration of a traced, non-captured join
+static void TR(const char* name) {
+    if (!g_tracing) return;
+    if (g.tr_n == g.tr_ev.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        g.tr_ev.push_back(e);
+        g.tr_name.push_back(name);
+    }
+    g.tr_name[g.tr_n] = name;
+    CK(cudaEventRecord(g.tr_ev[g.tr_n++], g.stream));
+}
+static void trace_print(int rank) {
+    for (size_t i = 1; i < g.tr_n; i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, g.tr_ev[i - 1], g.tr_ev[i]));
+        fprintf(stderr, "[hwbrj trace] rank %d  %-28s %8.3f ms\n", rank, g.tr_name[i], ms);
+    }
+    g.tr_n = 0;
 }
 
 // ---- kernel dispatch on the compile-time specialisations ---------------------------------------------------------------
@@ -333,11 +363,13 @@ static int run_probe(const uint2* dS, uint64_t nS, const unsigned long long* n_p
     bp.nranges = (uint32_t)nranges;
     if (nranges == 1) {
         launch_probe_mode(base_mode, dS, nS, n_ptr, bp, out, cursor);
+        TR("K2 probe");
         return 1;
     }
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
         launch_probe_mode(base_mode | 4, dS, nS, n_ptr, bp, out, cursor);
+        TR("K2 probe (range pass)");
     }
     return nranges;
 }
@@ -392,28 +424,35 @@ static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, con
     const uint32_t* hist_all = hist;
     if (f.world > 1) {
         k_push_rows<<<dim3(4, f.world), 256, 0, g.stream>>>(rows, (uint32_t)f.world, (uint32_t)f.rank, hist, P);
+        TR("push histogram rows");
         launch_barrier(f, ctrl);
+        TR("barrier");
         hist_all = reinterpret_cast<const uint32_t*>(rows.p[f.rank]);
         launches += 2;
     }
     k_scan_dist<<<1, 1024, 0, g.stream>>>(hist_all, (uint32_t)f.world, (uint32_t)f.rank, P, pf.b2, capacity, off,
                                           g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(), g.tiles.as<uint32_t>(), n_own,
                                           &ctrl->abort);
+    TR("K3 scan");
     launches++;
     uint2* t1 = recv.buf[f.rank];
     if (f.world > 1) {
         launch_scatter_l<1, true>(pmode, in, t1, n_ptr, n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pf, 1u << b1, 0u,
                                   recv, &ctrl->abort);
+        TR("K4 scatter level 1 (peer)");
         launch_barrier(f, ctrl);  // every rank's tuples have arrived
+        TR("barrier");
         launches += 2;
     } else {
         launch_scatter_l<1, false>(pmode, in, t1, n_ptr, n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pf, 1u << b1, 0u,
                                    recv, nullptr);
+        TR("K4 scatter level 1");
         launches++;
     }
     if (pf.b2 == 0) return t1;
     launch_scatter_l<2, false>(pmode, t1, t2, nullptr, capacity, off, g.tiles.as<uint32_t>(), g.cur2.as<uint32_t>(), pf,
                                1u << pf.b2, (1u << b1) / (uint32_t)f.world, recv, f.world > 1 ? &ctrl->abort : nullptr);
+    TR("K4 scatter level 2");
     launches++;
     return t2;
 }
@@ -543,6 +582,9 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
 
     // ---- timed region ----------------------------------------------------------------------------------------
     rec(1);
+    g_tracing = g.trace && mode != kCapture;
+    g.tr_n = 0;
+    TR("start");
     BloomParams bp;
     memset(&bp, 0, sizeof(bp));
     int nranges = 1;
@@ -557,10 +599,12 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         for (int r = 0; r < nranges; r++) {
             bp.range_id = (uint32_t)r;
             k_build_hist<true, 0><<<g.sms * 2, 1024, smem, g.stream>>>(dR, nR, nullptr, bp, g.d_crc, g.histR.as<uint32_t>(), pf);
+            TR("K1 insert + histogram R");
             launches++;
         }
     } else {
         launch_hist(pmode, dR, nR, nullptr, bp, g.histR.as<uint32_t>(), pf);
+        TR("K1 histogram R");
         launches++;
     }
     rec(2);
@@ -585,16 +629,19 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
                 if (dist) HWBRJ_K1P(false, true); else HWBRJ_K1P(false, false);
             }
 #undef HWBRJ_K1P
+            TR("K1' filter slices");
             launches++;
         } else if (dist) {  // partial filters are complete on every rank (the barrier after the level-1 scatter)
             const uint64_t n16 = std::max<uint64_t>(args->m / 8, 16) / 16;
             const uint64_t per = n16 / (uint64_t)f.world;
             k_filter_or_bcast<<<g.sms * 4, 256, 0, g.stream>>>(f.partial, f.filter, (uint32_t)f.world, per * f.rank,
                                                                f.rank == f.world - 1 ? n16 - per * f.rank : per);
+            TR("filter OR + broadcast");
             launches++;
         }
         if (dist) {
             launch_barrier(f, ctrl);  // the replicated filter is complete on every rank
+            TR("barrier");
             launches++;
         }
     }
@@ -618,6 +665,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     rec(5);  // ms_probe = the K2 launches only
     // partition histogram of the tuples that go on to the join (survivors, or all of S without a filter)
     launch_hist(pmode, Sin, nS, n_dev, bp, g.histS.as<uint32_t>(), pf);
+    TR("histogram S side");
     launches++;
     // one GPU with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc ; several GPUs: -> owner's recvS -> s2
     const uint2* Sp = run_partition(f, pmode, pf, Sin, nS, n_dev, g.histS.as<uint32_t>(), f.histS, recvS, dist ? f.cap_s : nS,
@@ -626,6 +674,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     rec(6);
     k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), PL, g.work.as<uint32_t>(),
                                          g.work_part.as<uint32_t>());
+    TR("work list");
     launches++;
     if (pmode != 0)
         k_join<true><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
@@ -635,6 +684,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         k_join<false><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
             Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), PL,
             (uint32_t)bits, &ctrl->item_counter, &ctrl->acc);
+    TR("K5 join");
     launches++;
     g.last_Rp = Rp;
     g.last_Sp = Sp;
@@ -651,9 +701,11 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         launch_barrier(f, ctrl);  // also: every rank has finished reading its receive buffers -> the next join may start
         k_reduce_rows<<<1, 32, 0, g.stream>>>(reinterpret_cast<const unsigned long long*>(f.rows.p[f.rank]), (uint32_t)f.world,
                                               ctrl->out);
+        TR("result rows: push + barrier + sum");
         launches += 3;
     }
     rec(8);
+    g_tracing = false;
     st.kernel_launches = launches;
     st.radix_bits = bits;
     st.range_passes = nranges;
@@ -673,6 +725,7 @@ static int collect_join(hwbrj_stats_t& st, bool has_filter) {
     CK(cudaMemcpyAsync(&h, g.ctrl.p, sizeof(Control), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaGetLastError());
+    if (g.trace) trace_print(st.n_gpus > 1 ? g.dev : 0);
     auto ms = [&](int a, int b) {
         float v = 0;
         CK(cudaEventElapsedTime(&v, g.ev[a], g.ev[b]));

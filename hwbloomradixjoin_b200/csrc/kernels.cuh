@@ -781,7 +781,6 @@ k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned 
           PeerBufs peers, const uint32_t* __restrict__ abort_flag) {
     constexpr int PER = kScatterTile / kScatterThreads;
     constexpr int NB = 1 << kMaxLevelBits;
-    constexpr bool kKeepBin = PMODE != 0;  // hash partitions: remember the bin; radix bins are recomputed from the key
     static_assert(kScatterThreads >= 32 + NB, "claims run on threads 32.. beside the scan warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* raw = reinterpret_cast<uint2*>(smem_raw);                       // [stages][kScatterStageTuples]
@@ -791,7 +790,8 @@ k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned 
     __shared__ uint32_t gclaim[NB];
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
-    __shared__ uint8_t sorted_bin[kKeepBin ? kScatterTile : 1];
+    __shared__ uint32_t sorted_dst[kScatterTile];  // output position of every sorted tuple (owner in the top bits when PEER)
+    __shared__ uint8_t sorted_own[(PEER && LEVEL == 1) ? kScatterTile : 1];
     __shared__ uint32_t crc_tab[PMODE == 2 ? kCrcSmemWords : 1];
     if (abort_flag && *abort_flag) return;  // a receive buffer would overflow (k_scan_dist): nothing is written
     const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;
@@ -869,27 +869,23 @@ k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned 
             gclaim[bb] = tot ? atomicAdd(&cursor[d.cbase + bb], tot) : 0u;
         }
         __syncthreads();  // (C)
+        // sort the tile by bin in shared memory; next to every tuple goes its final output position, so that the write-out
+        // below is two conflict-free shared loads and one coalesced store per tuple (no per-bin look-ups there)
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
-                uint32_t bin = rank[j] >> 24;
-                uint32_t pos = binstart[bin] + (rank[j] & 0xFFFFFFu);
+                const uint32_t bin = rank[j] >> 24, rk = rank[j] & 0xFFFFFFu;
+                const uint32_t pos = binstart[bin] + rk;
                 sorted[pos] = t[j];
-                if (kKeepBin) sorted_bin[pos] = (uint8_t)bin;
+                sorted_dst[pos] = gclaim[bin] + rk;
+                if (PEER && LEVEL == 1) sorted_own[pos] = (uint8_t)(bin >> peers.shift);
             }
         }
         __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
-            const uint2 tt = sorted[i];
-            uint32_t bin;
-            if (kKeepBin) bin = (uint32_t)sorted_bin[i];
-            else {
-                const uint32_t pid = pid_of<PMODE>(pf, crc_tab, tt.x);
-                bin = LEVEL == 1 ? pid >> b2 : pid & submask;
-            }
-            uint2* dst = (PEER && LEVEL == 1) ? peers.buf[bin >> peers.shift] : out;  // NVLink store when the owner is a peer
-            dst[gclaim[bin] + (i - binstart[bin])] = tt;
+            uint2* dst = (PEER && LEVEL == 1) ? peers.buf[sorted_own[i]] : out;  // NVLink store when the owner is a peer
+            dst[sorted_dst[i]] = sorted[i];
         }
         // next iteration: hist is rewritten before its first barrier, binstart/gclaim after (A'), sorted after (C'):
         // no thread can pass that first barrier before every thread has finished this write-out loop
@@ -945,14 +941,27 @@ __global__ void __launch_bounds__(512) k_filter_from_parts(const uint2* __restri
         }
         __syncthreads();  // slice complete
         const size_t first = (size_t)(gbase + p) * slice_words;
-        for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) {
-            const uint32_t w = sl[i];
-            if (PEER) {
-                for (uint32_t g = 0; g < world; g++) reinterpret_cast<uint32_t*>(filters.p[g])[first + i] = w;
-            } else {
-                reinterpret_cast<uint32_t*>(filters.p[0])[first + i] = w;
+        if ((slice_words & 3u) == 0u) {  // 16 bytes per thread and store: slices and filters are 16-byte aligned
+            uint4* sl4 = reinterpret_cast<uint4*>(sl);
+            for (uint32_t i = threadIdx.x; i < slice_words / 4u; i += blockDim.x) {
+                const uint4 w = sl4[i];
+                sl4[i] = make_uint4(0u, 0u, 0u, 0u);  // ready for a later partition
+                if (PEER) {
+                    for (uint32_t g = 0; g < world; g++) reinterpret_cast<uint4*>(filters.p[g])[first / 4 + i] = w;
+                } else {
+                    reinterpret_cast<uint4*>(filters.p[0])[first / 4 + i] = w;
+                }
             }
-            sl[i] = 0u;  // ready for a later partition; with two buffers the next partition uses the other one meanwhile
+        } else {
+            for (uint32_t i = threadIdx.x; i < slice_words; i += blockDim.x) {
+                const uint32_t w = sl[i];
+                if (PEER) {
+                    for (uint32_t g = 0; g < world; g++) reinterpret_cast<uint32_t*>(filters.p[g])[first + i] = w;
+                } else {
+                    reinterpret_cast<uint32_t*>(filters.p[0])[first + i] = w;
+                }
+                sl[i] = 0u;  // with two buffers the next partition uses the other one meanwhile
+            }
         }
         if (nbuf != 2) __syncthreads();
     }
