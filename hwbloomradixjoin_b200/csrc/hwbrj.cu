@@ -78,7 +78,7 @@ struct Control {
 struct Fab {
     int world = 1, rank = 0, gbits = 0;
     PeerPtrs flags, histR, histS, rows, filter, partial;
-    PeerBufs recvR, recvS;
+    PeerBufs stageR, stageS;  // level-1 outputs of all ranks: the level-2 pass reads its input segments from them
     uint32_t* epoch = nullptr;
     uint64_t cap_r = 0, cap_s = 0, filter_bytes = 0;
 };
@@ -92,7 +92,7 @@ struct Ctx {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[12];
     uint32_t* d_crc = nullptr;
-    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, work, work_part, ctrl, rt1, rp, sc, st1, s2, inR, inS, scratch;
+    DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, segs, work, work_part, ctrl, rt1, rp, sc, st1, s2, inR, inS, scratch;
     // state of the most recent join's partitions (inputs of a materialising k_join pass)
     const uint2* last_Rp = nullptr;
     const uint2* last_Sp = nullptr;
@@ -191,11 +191,8 @@ static void init_ctx() {
     // kernel attributes are per device: every instantiation the pipeline can launch is prepared here
     set_smem(k_build_hist<false, 0>, kHistSmem); set_smem(k_build_hist<false, 1>, kHistSmem);
     set_smem(k_build_hist<false, 2>, kHistSmem); set_smem(k_build_hist<true, 0>, kHistSmem);
-    set_smem(k_scatter<1, 0, false>, kScatterSmem); set_smem(k_scatter<1, 1, false>, kScatterSmem);
-    set_smem(k_scatter<1, 2, false>, kScatterSmem); set_smem(k_scatter<1, 0, true>, kScatterSmem);
-    set_smem(k_scatter<1, 1, true>, kScatterSmem);  set_smem(k_scatter<1, 2, true>, kScatterSmem);
-    set_smem(k_scatter<2, 0, false>, kScatterSmem); set_smem(k_scatter<2, 1, false>, kScatterSmem);
-    set_smem(k_scatter<2, 2, false>, kScatterSmem);
+    set_smem(k_scatter<1, 0>, kScatterSmem); set_smem(k_scatter<1, 1>, kScatterSmem); set_smem(k_scatter<1, 2>, kScatterSmem);
+    set_smem(k_scatter<2, 0>, kScatterSmem); set_smem(k_scatter<2, 1>, kScatterSmem); set_smem(k_scatter<2, 2>, kScatterSmem);
     set_smem(k_filter_from_parts<false, false>, kFilterSliceSmemMax); set_smem(k_filter_from_parts<false, true>, kFilterSliceSmemMax);
     set_smem(k_filter_from_parts<true, false>, kFilterSliceSmemMax);  set_smem(k_filter_from_parts<true, true>, kFilterSliceSmemMax);
     set_smem(k_join<false>, kJoinSmemBytes); set_smem(k_join<true>, kJoinSmemBytes);
@@ -204,7 +201,7 @@ static void init_ctx() {
     init_probe_mode<4>(); init_probe_mode<5>(); init_probe_mode<6>(); init_probe_mode<7>();
     set_smem(k_probe_staged<0>, kProbeWarps * kProbeSmemPerWarp); set_smem(k_probe_staged<1>, kProbeWarps * kProbeSmemPerWarp);
     set_smem(k_probe_staged<4>, kProbeWarps * kProbeSmemPerWarp); set_smem(k_probe_staged<5>, kProbeWarps * kProbeSmemPerWarp);
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter, k_scatter<1, 1, false>, kScatterThreads, kScatterSmem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter, k_scatter<1, 1>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join<false>, kJoinThreads, kJoinSmemBytes));
     g.occ_scatter = std::max(g.occ_scatter, 1);
     g.occ_join = std::max(g.occ_join, 1);
@@ -288,14 +285,16 @@ static int pick_bits(uint64_t nR, int gbits) {
     if (g.radix_bits_override > 0) b = std::min(g.radix_bits_override, (int)kMaxRadixBits);
     else
         while (b < kMaxRadixBits && (nR >> b) > (uint64_t)(kTableCap * 3 / 4)) b++;
+    // one scatter pass sorts a tile into at most 2^7 bins: NUM_PASSES = 1 caps the fan-out there (bigger partitions are
+    // joined in several table rounds), as the reference's single pass has to handle all NUM_RADIX_BITS at once
+    if (g.passes_override == 1) b = std::min(b, (int)kMaxLevelBits);
     return std::max(b, gbits);
 }
 // level-2 bits (the reference's NUM_PASSES, prj_params.h:20-22; HWBRJ_NUM_PASSES / hwbrj_set_num_passes override):
 // one pass while the fan-out fits one scatter pass, else two passes of about equal width
 static int pick_b2(int bits, int gbits) {
     int passes = g.passes_override;
-    if (passes == 1 && bits > kMaxLevelBits) passes = 2;  // one pass cannot exceed 2^7 bins
-    if (passes <= 0) passes = bits > kMaxLevelBits ? 2 : 1;
+    if (passes <= 0 || bits > kMaxLevelBits) passes = bits > kMaxLevelBits ? 2 : (passes <= 0 ? 1 : passes);
     if (passes == 1 || bits < 2) return 0;
     int b2 = std::min(bits / 2, bits - gbits);  // the owner is a prefix of the level-1 bin
     if (const char* s = getenv("HWBRJ_L1_BITS")) b2 = bits - std::max(gbits, std::min(atoi(s), bits));  // experiments
@@ -385,25 +384,24 @@ static void launch_hist(int pmode, const uint2* in, uint64_t n, const unsigned l
     }
 }
 
-template <int LEVEL, bool PEER>
-static void launch_scatter_l(int pmode, const uint2* in, uint2* out, const unsigned long long* n_ptr, uint64_t n,
-                             const uint32_t* off, const uint32_t* tiles, uint32_t* cursor, const PartFn& pf, uint32_t nbins,
-                             uint32_t P1L, const PeerBufs& peers, const uint32_t* abort_flag) {
+template <int LEVEL>
+static void launch_scatter_l(int pmode, const uint2* in, const PeerBufs& stages, uint2* out, const unsigned long long* n_ptr,
+                             uint64_t n, uint32_t* cursor, const PartFn& pf, uint32_t nbins, uint32_t nseg, uint32_t G,
+                             const uint32_t* abort_flag) {
     const int grid = g.sms * g.occ_scatter;
+    const uint32_t* tiles = g.tiles.as<uint32_t>();
+    const uint32_t* seg_start = g.segs.as<uint32_t>();
+    const uint32_t* seg_cnt = seg_start + (1u << kMaxLevelBits);
+#define HWBRJ_SCATTER(PM)                                                                                              \
+    k_scatter<LEVEL, PM><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, stages, out, n_ptr, n, tiles, seg_start,  \
+                                                                           seg_cnt, cursor, pf, g.d_crc, nbins, nseg, G, \
+                                                                           abort_flag)
     switch (pmode) {
-        case 0:
-            k_scatter<LEVEL, 0, PEER><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, out, n_ptr, n, off, tiles, cursor, pf,
-                                                                                        g.d_crc, nbins, P1L, peers, abort_flag);
-            break;
-        case 1:
-            k_scatter<LEVEL, 1, PEER><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, out, n_ptr, n, off, tiles, cursor, pf,
-                                                                                        g.d_crc, nbins, P1L, peers, abort_flag);
-            break;
-        default:
-            k_scatter<LEVEL, 2, PEER><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, out, n_ptr, n, off, tiles, cursor, pf,
-                                                                                        g.d_crc, nbins, P1L, peers, abort_flag);
-            break;
+        case 0: HWBRJ_SCATTER(0); break;
+        case 1: HWBRJ_SCATTER(1); break;
+        default: HWBRJ_SCATTER(2); break;
     }
+#undef HWBRJ_SCATTER
 }
 
 static void launch_barrier(const Fab& f, Control* ctrl) {
@@ -412,17 +410,19 @@ static void launch_barrier(const Fab& f, Control* ctrl) {
                                       2ll * g.clock_khz * 1000ll);
 }
 
-// histogram rows of all ranks -> offsets; scatter level 1 (into the owners' buffers) and level 2 (local).
-// Returns the final partitions of this rank. `hist` is this rank's row (already computed); `rows` where every rank's row
-// is gathered (world > 1), `recv` the level-1 destination of every owner, `t2` the local level-2 output.
+// Histogram rows of all ranks -> offsets; level-1 scatter of this rank's chunk into its staging buffer (local); level-2
+// scatter of the OWNED level-1 bins, which pulls its input segments from the staging buffers of all ranks. Returns the
+// final partitions of this rank. `hist` is this rank's row (already computed), `rows` where every rank's row is gathered
+// (world > 1), `stages` the staging buffers, `t2` the local level-2 output, `capacity` bounds a chunk and an owner's share.
 static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, const uint2* in, uint64_t n,
                                   const unsigned long long* n_ptr, uint32_t* hist, const PeerPtrs& rows,
-                                  const PeerBufs& recv, uint64_t capacity, uint32_t* off, uint2* t2,
+                                  const PeerBufs& stages, uint64_t capacity, uint32_t* off, uint2* t2,
                                   unsigned long long* n_own, Control* ctrl, int& launches) {
     const uint32_t P = 1u << pf.bits;
     const uint32_t b1 = pf.bits - pf.b2;
+    const bool dist = f.world > 1;
     const uint32_t* hist_all = hist;
-    if (f.world > 1) {
+    if (dist) {
         k_push_rows<<<dim3(4, f.world), 256, 0, g.stream>>>(rows, (uint32_t)f.world, (uint32_t)f.rank, hist, P);
         TR("push histogram rows");
         launch_barrier(f, ctrl);
@@ -430,29 +430,28 @@ static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, con
         hist_all = reinterpret_cast<const uint32_t*>(rows.p[f.rank]);
         launches += 2;
     }
+    uint32_t* seg_start = g.segs.as<uint32_t>();
     k_scan_dist<<<1, 1024, 0, g.stream>>>(hist_all, (uint32_t)f.world, (uint32_t)f.rank, P, pf.b2, capacity, off,
-                                          g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(), g.tiles.as<uint32_t>(), n_own,
-                                          &ctrl->abort);
+                                          g.cur1.as<uint32_t>(), g.cur2.as<uint32_t>(), g.tiles.as<uint32_t>(), seg_start,
+                                          seg_start + (1u << kMaxLevelBits), n_own, &ctrl->abort);
     TR("K3 scan");
     launches++;
-    uint2* t1 = recv.buf[f.rank];
-    if (f.world > 1) {
-        launch_scatter_l<1, true>(pmode, in, t1, n_ptr, n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pf, 1u << b1, 0u,
-                                  recv, &ctrl->abort);
-        TR("K4 scatter level 1 (peer)");
-        launch_barrier(f, ctrl);  // every rank's tuples have arrived
+    uint2* t1 = stages.buf[f.rank];
+    launch_scatter_l<1>(pmode, in, stages, t1, n_ptr, n, g.cur1.as<uint32_t>(), pf, 1u << b1, 0u, 1u,
+                        dist ? &ctrl->abort : nullptr);
+    TR("K4 scatter level 1");
+    launches++;
+    if (dist) {
+        launch_barrier(f, ctrl);  // every rank's staging buffer is complete
         TR("barrier");
-        launches += 2;
-    } else {
-        launch_scatter_l<1, false>(pmode, in, t1, n_ptr, n, off, g.tiles.as<uint32_t>(), g.cur1.as<uint32_t>(), pf, 1u << b1, 0u,
-                                   recv, nullptr);
-        TR("K4 scatter level 1");
         launches++;
+    } else if (pf.b2 == 0) {
+        return t1;  // one GPU, one pass: the level-1 output is final
     }
-    if (pf.b2 == 0) return t1;
-    launch_scatter_l<2, false>(pmode, t1, t2, nullptr, capacity, off, g.tiles.as<uint32_t>(), g.cur2.as<uint32_t>(), pf,
-                               1u << pf.b2, (1u << b1) / (uint32_t)f.world, recv, f.world > 1 ? &ctrl->abort : nullptr);
-    TR("K4 scatter level 2");
+    // several GPUs: always (with b2 == 0 it degenerates to gathering the owned bins from the peers)
+    launch_scatter_l<2>(pmode, nullptr, stages, t2, nullptr, capacity, g.cur2.as<uint32_t>(), pf, 1u << pf.b2, 1u << b1,
+                        (uint32_t)f.world, dist ? &ctrl->abort : nullptr);
+    TR(dist ? "K4 scatter level 2 (pull)" : "K4 scatter level 2");
     launches++;
     return t2;
 }
@@ -467,6 +466,7 @@ static void ensure_workspace(uint64_t capR, uint64_t nS, uint64_t capS, const bl
     g.cur1.ensure(((size_t)1 << kMaxLevelBits) * 4);
     g.cur2.ensure(P * 4);
     g.tiles.ensure((((size_t)1 << kMaxLevelBits) + 1) * 4);
+    g.segs.ensure(((size_t)2 << kMaxLevelBits) * 4);
     g.work.ensure((P + 1) * 4);
     g.work_part.ensure((P + capS / kSChunk + 2) * 4);  // one entry per join work item
     g.ctrl.ensure(sizeof(Control));
@@ -559,16 +559,15 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         pf.size_mask = (uint32_t)(args->m / args->B - 1);
         pf.hshift = (uint32_t)(ilog2_u64(args->m / args->B) - bits);
     }
-    // level-1 receive buffers and filters: the symmetric memory of the GPU group, or the plain workspace
-    PeerBufs recvR = f.recvR, recvS = f.recvS;
+    // level-1 staging buffers and filters: the symmetric memory of the GPU group, or the plain workspace
+    PeerBufs stageR = f.stageR, stageS = f.stageS;
     PeerPtrs filt = f.filter;
     uint32_t* my_filter = nullptr;
     if (!dist) {
-        recvR.buf[0] = g.rt1.as<uint2>();
-        recvS.buf[0] = g.st1.as<uint2>();
+        stageR.buf[0] = g.rt1.as<uint2>();
+        stageS.buf[0] = g.st1.as<uint2>();
         filt.p[0] = g.filter.p;
     }
-    recvR.shift = recvS.shift = (uint32_t)(bits - b2 - f.gbits);
     if (args) my_filter = reinterpret_cast<uint32_t*>(filt.p[f.rank]);
     // non-sliceable filter on several GPUs: every rank inserts its R chunk into a full-size partial, then OR-combine
     uint32_t* insert_filter = (args && pmode == 0 && dist) ? reinterpret_cast<uint32_t*>(f.partial.p[f.rank]) : my_filter;
@@ -608,7 +607,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         launches++;
     }
     rec(2);
-    const uint2* Rp = run_partition(f, pmode, pf, dR, nR, nullptr, g.histR.as<uint32_t>(), f.histR, recvR,
+    const uint2* Rp = run_partition(f, pmode, pf, dR, nR, nullptr, g.histR.as<uint32_t>(), f.histR, stageR,
                                     dist ? f.cap_r : nR, g.offR.as<uint32_t>(), g.rp.as<uint2>(), &ctrl->n_own_r, ctrl,
                                     launches);
     rec(3);
@@ -667,8 +666,8 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     launch_hist(pmode, Sin, nS, n_dev, bp, g.histS.as<uint32_t>(), pf);
     TR("histogram S side");
     launches++;
-    // one GPU with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc ; several GPUs: -> owner's recvS -> s2
-    const uint2* Sp = run_partition(f, pmode, pf, Sin, nS, n_dev, g.histS.as<uint32_t>(), f.histS, recvS, dist ? f.cap_s : nS,
+    // one GPU with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc ; several GPUs: sc -> own staging -> (pull) -> s2
+    const uint2* Sp = run_partition(f, pmode, pf, Sin, nS, n_dev, g.histS.as<uint32_t>(), f.histS, stageS, dist ? f.cap_s : nS,
                                     g.offS.as<uint32_t>(), dist ? g.s2.as<uint2>() : g.sc.as<uint2>(), &ctrl->n_own_s, ctrl,
                                     launches);
     rec(6);
@@ -897,8 +896,8 @@ static int dist_connect(hwbrj_dist* d, const void* all_handles) {
         f.rows.p[r] = d->peer[r] + d->off_rows;
         f.filter.p[r] = d->peer[r] + d->off_filter;
         f.partial.p[r] = d->peer[r] + d->off_partial;
-        f.recvR.buf[r] = reinterpret_cast<uint2*>(d->peer[r] + d->off_recvR);
-        f.recvS.buf[r] = reinterpret_cast<uint2*>(d->peer[r] + d->off_recvS);
+        f.stageR.buf[r] = reinterpret_cast<uint2*>(d->peer[r] + d->off_recvR);
+        f.stageS.buf[r] = reinterpret_cast<uint2*>(d->peer[r] + d->off_recvS);
     }
     f.epoch = reinterpret_cast<uint32_t*>(d->base + d->off_epoch);
     f.cap_r = d->cap_r;
@@ -1518,11 +1517,10 @@ static const uint2* partition_local(int pmode, const PartFn& pf, const uint2* in
     memset(&bp, 0, sizeof(bp));
     launch_hist(pmode, in, n, nullptr, bp, g.histR.as<uint32_t>(), pf);
     Fab f = single_fab();
-    PeerBufs recv;
-    memset(&recv, 0, sizeof(recv));
-    recv.buf[0] = g.rt1.as<uint2>();
-    recv.shift = pf.bits - pf.b2;
-    return run_partition(f, pmode, pf, in, n, nullptr, g.histR.as<uint32_t>(), f.histR, recv, n, g.offR.as<uint32_t>(),
+    PeerBufs stage;
+    memset(&stage, 0, sizeof(stage));
+    stage.buf[0] = g.rt1.as<uint2>();
+    return run_partition(f, pmode, pf, in, n, nullptr, g.histR.as<uint32_t>(), f.histR, stage, n, g.offR.as<uint32_t>(),
                          g.rp.as<uint2>(), &ctrl->n_own_r, ctrl, launches);
 }
 

@@ -515,13 +515,16 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
 // are the G ranks here. One CTA of 1024 threads; P <= 2^14 partitions, of which rank g owns the contiguous range
 // [g*P/G, (g+1)*P/G). hist_all[src][p] = number of tuples of partition p in rank src's input (every rank holds all G
 // rows: they are pushed over NVLink by k_push_rows; G == 1: the row is the local histogram). From these the kernel derives
-//   * send cursors cursor1[B] for every GLOBAL level-1 bin B: this rank's first write position for bin B inside the
-//     receive buffer of B's owner = start of the bin there + tuples the ranks before this one send to it. Every rank
-//     computes the same layout, so the level-1 scatter stores straight into peer memory without any remote atomic;
-//   * for the OWNED partitions: fine_off[PL+1] (boundaries, in increasing pid order -- the reference's cluster order,
-//     :1896-1939), the level-2 cursors, and the tile schedule of the level-2 pass (tile_off[P1L+1]);
-//   * n_own = tuples this rank owns; *abort = 1 if any owner would receive more than `capacity` tuples: then the
-//     scatter kernels store nothing and every partition is declared empty (the join reports the failure).
+//   * cursor1[B] for every GLOBAL level-1 bin B: where this rank's level-1 scatter puts bin B in its OWN staging buffer
+//     (an exclusive scan of its own row: the level-1 pass is purely local);
+//   * the level-2 input segments of the OWNED level-1 bins: segment (lb, src) = the tuples of owned bin lb that sit in
+//     rank src's staging buffer, seg_start[lb*G+src] tuples into it (src's cursor1, which every rank can compute).
+//     The level-2 pass PULLS these segments over NVLink with bulk loads, so every tuple crosses the fabric exactly once,
+//     in large sequential reads, and nothing is ever written into a peer's partitions;
+//   * the tile schedule of that pass (tile_off[P1+1] over the P1 = P1L*G segments), the fine boundaries fine_off[PL+1] of
+//     the owned partitions (in increasing pid order -- the reference's cluster order, :1896-1939) and the level-2 cursors;
+//   * n_own = tuples this rank owns; *abort = 1 if a rank's chunk or an owner's share exceeds `capacity`: then every
+//     partition is declared empty and the scatter kernels do nothing (the join reports the failure).
 constexpr int kBinsPerThread = (1 << kMaxRadixBits) / 1024;
 
 // exclusive block scan of one value per thread (1024 threads); returns the exclusive prefix, total via warp_sums[32]
@@ -554,14 +557,15 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const uint32_t* __restrict__
                                                    uint32_t P, uint32_t b2, unsigned long long capacity,
                                                    uint32_t* __restrict__ fine_off, uint32_t* __restrict__ cursor1,
                                                    uint32_t* __restrict__ cursor2, uint32_t* __restrict__ tile_off,
+                                                   uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_cnt,
                                                    unsigned long long* __restrict__ n_own, uint32_t* __restrict__ abort) {
+    constexpr uint32_t NB = 1u << kMaxLevelBits;
     __shared__ uint32_t warp_sums[33];
-    __shared__ unsigned long long s_bucket[kMaxPeers][1 << kMaxLevelBits];  // tuples rank src sends to level-1 bin B
-    __shared__ unsigned long long s_bstart[(1 << kMaxLevelBits)];           // start of bin B in its owner's buffer
-    __shared__ unsigned long long s_btot[(1 << kMaxLevelBits)];
+    __shared__ unsigned long long s_bucket[kMaxPeers][NB];  // tuples of level-1 bin B in rank src's chunk
+    __shared__ unsigned long long s_lstart[kMaxPeers][NB];  // start of bin B in src's staging buffer (src-local scan)
     __shared__ uint32_t s_abort;
     const uint32_t P1 = P >> b2, PL = P / G, P1L = P1 / G;
-    for (uint32_t i = threadIdx.x; i < G * (1u << kMaxLevelBits); i += 1024u) (&s_bucket[0][0])[i] = 0ull;
+    for (uint32_t i = threadIdx.x; i < G * NB; i += 1024u) (&s_bucket[0][0])[i] = 0ull;
     if (threadIdx.x == 0) s_abort = *abort;  // the other relation of this join may already have overflowed
     __syncthreads();
     const uint32_t per = (P + 1023u) / 1024u;  // a power of two <= 2^b2 whenever P > 1024, else 1
@@ -586,34 +590,29 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const uint32_t* __restrict__
         }
     }
     __syncthreads();
-    if (threadIdx.x < P1) {
-        unsigned long long t = 0;
-        for (uint32_t src = 0; src < G; src++) t += s_bucket[src][threadIdx.x];
-        s_btot[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x < G) {  // one thread per owner: exclusive scan over its <= 128 level-1 bins
+    if (threadIdx.x < G) {  // one thread per rank: exclusive scan of its row over the <= 128 level-1 bins
         unsigned long long run = 0;
-        for (uint32_t lb = 0; lb < P1L; lb++) {
-            s_bstart[threadIdx.x * P1L + lb] = run;
-            run += s_btot[threadIdx.x * P1L + lb];
+        for (uint32_t B = 0; B < P1; B++) {
+            s_lstart[threadIdx.x][B] = run;
+            run += s_bucket[threadIdx.x][B];
         }
-        if (run > capacity) {
-            *abort = 1u;
-            s_abort = 1u;
-        }
-        if (threadIdx.x == rank) *n_own = run;
+        if (run > capacity) s_abort = 1u;  // its chunk does not fit its staging buffer
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + G) {  // one thread per owner: what it will own
+        const uint32_t o = threadIdx.x - 32u;
+        unsigned long long own = 0;
+        for (uint32_t lb = 0; lb < P1L; lb++)
+            for (uint32_t src = 0; src < G; src++) own += s_bucket[src][o * P1L + lb];
+        if (own > capacity) s_abort = 1u;
+        if (o == rank) *n_own = own;
     }
     __syncthreads();
-    // an overflow anywhere (every rank sees the same rows, so all ranks agree): the scatter kernels write nothing and the
-    // owned partitions are declared empty, so that nothing downstream reads past a buffer
+    // every rank sees the same rows, so all ranks agree on an overflow
     const bool dead = s_abort != 0u;
-    if (dead && threadIdx.x == 0) *n_own = 0ull;
-    if (threadIdx.x < P1) {
-        unsigned long long before = 0;
-        for (uint32_t src = 0; src < rank; src++) before += s_bucket[src][threadIdx.x];
-        cursor1[threadIdx.x] = (uint32_t)(s_bstart[threadIdx.x] + before);
+    if (dead && threadIdx.x == 0) {
+        *abort = 1u;
+        *n_own = 0ull;
     }
+    if (threadIdx.x < P1) cursor1[threadIdx.x] = (uint32_t)s_lstart[rank][threadIdx.x];
     // fine offsets of the owned partitions (contiguous thread range: other threads contribute 0)
     uint32_t local = 0;
 #pragma unroll
@@ -635,12 +634,17 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const uint32_t* __restrict__
     }
     if (threadIdx.x == 0) fine_off[PL] = warp_sums[32];
     __syncthreads();
-    // level-2 tile schedule over the owned level-1 bins, scanned by the same block scan
-    const uint32_t tiles = (threadIdx.x < P1L && !dead)
-                               ? (uint32_t)((s_btot[rank * P1L + threadIdx.x] + kScatterTile - 1) / kScatterTile)
-                               : 0u;
+    // level-2 input segments (owned bin lb, source rank src) and their tile schedule, scanned by the same block scan
+    uint32_t tiles = 0;
+    if (threadIdx.x < P1) {
+        const uint32_t lb = threadIdx.x / G, src = threadIdx.x % G, B = rank * P1L + lb;
+        const uint32_t cnt = dead ? 0u : (uint32_t)s_bucket[src][B];
+        seg_start[threadIdx.x] = (uint32_t)s_lstart[src][B];
+        seg_cnt[threadIdx.x] = cnt;
+        tiles = (cnt + kScatterTile - 1) / kScatterTile;
+    }
     const uint32_t tex = block_exclusive_scan_1024(tiles, warp_sums);
-    if (threadIdx.x <= P1L) tile_off[threadIdx.x] = tex;  // thread P1L has tiles == 0: its prefix is the grand total
+    if (threadIdx.x <= P1) tile_off[threadIdx.x] = tex;  // thread P1 has tiles == 0: its prefix is the grand total
 }
 
 // ---- small peer-memory collectives (NVLink / NVSwitch, no host involvement) --------------------------------------------
@@ -725,42 +729,52 @@ __global__ void k_filter_or(uint4* __restrict__ dst, const uint4* __restrict__ s
 // ---- K4: scatter with shared-memory staging ---------------------------------------------------------------------
 // replaces the scatter loop (:842-849) and pass-2 radix_cluster (:574-608).
 // Persistent CTAs; every CTA walks its tiles of kScatterTile tuples through a kScatterStages-deep ring of TMA
-// bulk loads (cp.async.bulk -> mbarrier), so the HBM read of the next tiles is in flight while the current tile
+// bulk loads (cp.async.bulk -> mbarrier), so the read of the next tiles is in flight while the current tile
 // is sorted by destination bin in shared memory (block-level shared atomics -> ranks), claims one contiguous range per
 // non-empty bin from the cursors and writes every bin's run with coalesced stores.
-// LEVEL 1: input = a whole relation (this rank's chunk), bin = pid >> b2 (a GLOBAL level-1 bin), cursor index = bin.
-//          PEER: the run goes to the receive buffer of the bin's owner GPU (peer memory over NVLink); the cursors were
-//          pre-computed from the all-gathered histograms (k_scan_dist), so the claim is a LOCAL atomic: the kernel is
-//          a fused partition + all-to-all with no remote atomics, no send buffers and no collective call.
-// LEVEL 2: input = the owned level-1 bins, work item = (bin, tile) from tile_off, bin = pid & (2^b2-1),
-//          cursor index = local pid.
+// LEVEL 1: input = a whole relation (this rank's chunk), bin = pid >> b2 (a GLOBAL level-1 bin), cursor index = bin,
+//          output = this rank's staging buffer (peer-mapped memory when several GPUs join).
+// LEVEL 2: input = the segments of the OWNED level-1 bins in the staging buffers of ALL ranks (k_scan_dist): the bulk
+//          loads of a tile read peer memory over NVLink, so this kernel is a fused all-to-all + partition pass -- no send
+//          or receive buffers, no remote stores or atomics, no collective call; every tuple crosses NVLink once, as part
+//          of a large sequential read. Work item = (segment, tile) from tile_off, bin = pid & (2^b2-1), cursor index =
+//          local pid, output = this rank's partitions.
 struct ScatterItem {
     uint64_t src_al;   // first tuple index of the bulk load (even: 16-byte aligned)
     uint32_t skip;     // 0/1 tuples to skip at the head of the staged tile
     uint32_t cnt;      // tuples of this tile
     uint32_t cbase;    // cursor base index
     uint32_t bytes;    // bulk-load size
+    uint32_t src;      // LEVEL 2: rank whose staging buffer holds the tile
+};
+
+struct PeerBufs {
+    uint2* buf[kMaxPeers];  // staging buffers of all ranks (peer device pointers mapped into this process)
 };
 
 template <int LEVEL>
-__device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ fine_off,
-                                                    const uint32_t* __restrict__ tile_off, uint32_t P1L, uint32_t b2) {
+__device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ tile_off,
+                                                    const uint32_t* __restrict__ seg_start,
+                                                    const uint32_t* __restrict__ seg_cnt, uint32_t nseg, uint32_t G,
+                                                    uint32_t b2) {
     ScatterItem it;
     uint64_t src0;
     if (LEVEL == 1) {
         src0 = item * kScatterTile;
         it.cnt = (uint32_t)min((uint64_t)kScatterTile, n - src0);
         it.cbase = 0u;
+        it.src = 0u;
     } else {
-        uint32_t lo = 0, hi = P1L;  // bin j with tile_off[j] <= item < tile_off[j+1]
+        uint32_t lo = 0, hi = nseg;  // segment j with tile_off[j] <= item < tile_off[j+1]
         while (hi - lo > 1u) {
             uint32_t mid = (lo + hi) >> 1;
             if (tile_off[mid] <= (uint32_t)item) lo = mid; else hi = mid;
         }
-        uint32_t bstart = fine_off[lo << b2], bend = fine_off[(lo + 1u) << b2];
-        src0 = (uint64_t)bstart + (uint64_t)((uint32_t)item - tile_off[lo]) * kScatterTile;
-        it.cnt = min((uint32_t)kScatterTile, bend - (uint32_t)src0);
-        it.cbase = lo << b2;
+        const uint32_t first = ((uint32_t)item - tile_off[lo]) * kScatterTile;
+        src0 = (uint64_t)seg_start[lo] + first;
+        it.cnt = min((uint32_t)kScatterTile, seg_cnt[lo] - first);
+        it.cbase = (lo / G) << b2;
+        it.src = lo % G;
     }
     it.skip = (uint32_t)(src0 & 1ull);
     it.src_al = src0 - it.skip;
@@ -768,17 +782,13 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
     return it;
 }
 
-struct PeerBufs {
-    uint2* buf[kMaxPeers];  // receive buffers (peer device pointers mapped into this process; buf[rank] is local)
-    uint32_t shift;         // owner of level-1 bin B = B >> shift
-};
-
-template <int LEVEL, int PMODE, bool PEER>
+template <int LEVEL, int PMODE>
 __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS)
-k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned long long* __restrict__ n_ptr,
-          uint64_t n_static, const uint32_t* __restrict__ fine_off, const uint32_t* __restrict__ tile_off,
-          uint32_t* __restrict__ cursor, PartFn pf, const uint32_t* __restrict__ g_crc, uint32_t nbins, uint32_t P1L,
-          PeerBufs peers, const uint32_t* __restrict__ abort_flag) {
+k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out,
+          const unsigned long long* __restrict__ n_ptr, uint64_t n_static, const uint32_t* __restrict__ tile_off,
+          const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_cnt, uint32_t* __restrict__ cursor,
+          PartFn pf, const uint32_t* __restrict__ g_crc, uint32_t nbins, uint32_t nseg, uint32_t G,
+          const uint32_t* __restrict__ abort_flag) {
     constexpr int PER = kScatterTile / kScatterThreads;
     constexpr int NB = 1 << kMaxLevelBits;
     static_assert(kScatterThreads >= 32 + NB, "claims run on threads 32.. beside the scan warp");
@@ -790,14 +800,13 @@ k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned 
     __shared__ uint32_t gclaim[NB];
     __shared__ __align__(8) uint64_t mbar[kScatterStages];
     __shared__ ScatterItem desc[kScatterStages];
-    __shared__ uint32_t sorted_dst[kScatterTile];  // output position of every sorted tuple (owner in the top bits when PEER)
-    __shared__ uint8_t sorted_own[(PEER && LEVEL == 1) ? kScatterTile : 1];
+    __shared__ uint8_t sorted_bin[kScatterTile];
     __shared__ uint32_t crc_tab[PMODE == 2 ? kCrcSmemWords : 1];
-    if (abort_flag && *abort_flag) return;  // a receive buffer would overflow (k_scan_dist): nothing is written
+    if (abort_flag && *abort_flag) return;  // a buffer would overflow (k_scan_dist): nothing is read or written
     const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;
     const uint32_t b2 = pf.b2;
     const uint32_t submask = (1u << b2) - 1u;
-    const uint64_t nitems = LEVEL == 1 ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[P1L];
+    const uint64_t nitems = LEVEL == 1 ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[nseg];
     if (PMODE == 2) load_crc_tab(crc_tab, g_crc);
     if (threadIdx.x == 0) {
         for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
@@ -805,10 +814,11 @@ k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned 
     }
     __syncthreads();
     auto issue = [&](uint64_t item, int st) {  // thread 0 only
-        ScatterItem it = scatter_item<LEVEL>(item, n, fine_off, tile_off, P1L, b2);
+        ScatterItem it = scatter_item<LEVEL>(item, n, tile_off, seg_start, seg_cnt, nseg, G, b2);
         desc[st] = it;
+        const uint2* base = LEVEL == 1 ? in : stages.buf[it.src];  // LEVEL 2: a bulk read over NVLink when src is a peer
         mbar_arrive_expect_tx(&mbar[st], it.bytes);
-        bulk_g2s(raw + st * kScatterStageTuples, in + it.src_al, it.bytes, &mbar[st]);
+        bulk_g2s(raw + st * kScatterStageTuples, base + it.src_al, it.bytes, &mbar[st]);
     };
     if (threadIdx.x == 0)
         for (int st = 0; st < kScatterStages; st++) {
@@ -869,23 +879,22 @@ k_scatter(const uint2* __restrict__ in, uint2* __restrict__ out, const unsigned 
             gclaim[bb] = tot ? atomicAdd(&cursor[d.cbase + bb], tot) : 0u;
         }
         __syncthreads();  // (C)
-        // sort the tile by bin in shared memory; next to every tuple goes its final output position, so that the write-out
-        // below is two conflict-free shared loads and one coalesced store per tuple (no per-bin look-ups there)
+        // sort the tile by bin in shared memory (the bin travels with the tuple: recomputing a hash bin costs more than a
+        // byte of shared memory; a 4-byte output position per tuple instead was measured slower -- it costs a CTA per SM)
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint32_t idx = threadIdx.x + j * kScatterThreads;
             if (idx < cnt) {
-                const uint32_t bin = rank[j] >> 24, rk = rank[j] & 0xFFFFFFu;
-                const uint32_t pos = binstart[bin] + rk;
+                const uint32_t bin = rank[j] >> 24;
+                const uint32_t pos = binstart[bin] + (rank[j] & 0xFFFFFFu);
                 sorted[pos] = t[j];
-                sorted_dst[pos] = gclaim[bin] + rk;
-                if (PEER && LEVEL == 1) sorted_own[pos] = (uint8_t)(bin >> peers.shift);
+                sorted_bin[pos] = (uint8_t)bin;
             }
         }
         __syncthreads();  // (D)
         for (uint32_t i = threadIdx.x; i < cnt; i += kScatterThreads) {
-            uint2* dst = (PEER && LEVEL == 1) ? peers.buf[sorted_own[i]] : out;  // NVLink store when the owner is a peer
-            dst[sorted_dst[i]] = sorted[i];
+            const uint32_t bin = sorted_bin[i];
+            out[gclaim[bin] + (i - binstart[bin])] = sorted[i];
         }
         // next iteration: hist is rewritten before its first barrier, binstart/gclaim after (A'), sorted after (C'):
         // no thread can pass that first barrier before every thread has finished this write-out loop

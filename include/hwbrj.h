@@ -143,8 +143,9 @@ int      hwbrj_last_filter(unsigned char * bitmap_out, uint64_t nbytes);
 void hwbrj_set_quiet(int quiet);    /* 1: suppress the reference-style stdout lines */
 /* tuning knobs (also read from env HWBRJ_RADIX_BITS / HWBRJ_NUM_PASSES / HWBRJ_RANGE_PASSES); 0 = automatic.
  * radix_bits and num_passes are the runtime form of the reference's compile-time NUM_RADIX_BITS / NUM_PASSES
- * (prj_params.h:15-22, swept by measurements/run.py:205-269): total partition bits (<= 14) and 1 or 2 scatter passes
- * (one pass handles at most 7 bits; more bits always take two). */
+ * (prj_params.h:15-22, swept by measurements/run.py:205-269): total partition bits (<= 14) and 1 or 2 scatter passes.
+ * One pass handles at most 7 bits, so num_passes = 1 caps the fan-out at 2^7 partitions; partitions that do not fit one
+ * shared-memory table are joined in several table rounds (results are independent of both knobs). */
 void hwbrj_set_radix_bits(int bits);
 void hwbrj_set_num_passes(int passes);
 void hwbrj_set_range_passes(int passes);
@@ -219,18 +220,22 @@ int hwbrj_radix_partition(const tuple_t * in, uint64_t n, int bits, tuple_t * ou
 /* ---- the multi-GPU join: one rank per GPU -------------------------------------------------------------
  * The join shards on the HIGH bits of the partition id: rank g owns partitions [g*P/G, (g+1)*P/G) -- for a BASIC (k <= 1)
  * or BLOCKED filter these are the keys whose filter bits lie in the g-th 1/G slice of the filter. Per rank and join:
- *   histogram of the local R chunk -> rows all-gathered over NVLink -> every rank derives where its tuples go ->
- *   level-1 scatter stores straight into the owners' receive buffers (fused partition + all-to-all, no remote atomics) ->
- *   level-2 scatter + filter-slice build in shared memory, each slice stored into EVERY rank's filter (fused build +
- *   all-gather) -> probe of the local S chunk against the replicated filter -> only the survivors are routed the same
- *   way -> per-partition build + probe on the owner -> result words all-gathered and summed.
+ *   histogram of the local R chunk -> rows all-gathered over NVLink -> every rank derives the layout of every rank's
+ *   level-1 output -> level-1 scatter of the local chunk into a peer-mapped staging buffer (purely local) -> the level-2
+ *   scatter of each owner PULLS the segments of its bins from all staging buffers with bulk loads over NVLink (fused
+ *   all-to-all + partition pass: every tuple crosses the fabric once, no send/receive buffers, no remote atomics) ->
+ *   filter-slice build in shared memory, each slice stored into EVERY rank's filter (fused build + all-gather) -> probe of
+ *   the local S chunk against the replicated filter -> only the survivors are partitioned and pulled the same way ->
+ *   per-partition build + probe on the owner -> result words all-gathered and summed.
  * All exchanges are peer-memory loads/stores issued by the kernels themselves; ranks meet at device-side barriers.
  * A rank is a process with one GPU (handles travel through the launcher's channel, e.g. torch.distributed.all_gather or
  * MPI) or one of several GPUs driven by one process (hwbrj_set_gpus does all of this internally). */
 typedef struct hwbrj_dist hwbrj_dist_t;
 #define HWBRJ_DIST_HANDLE_BYTES 128
-/* allocate this rank's symmetric block on the CURRENT device: receive buffers of cap_r / cap_s tuples and room for a filter
- * of max_filter_bytes; writes the handle peers need (HWBRJ_DIST_HANDLE_BYTES) to handle_out. world: power of two <= 16. */
+/* allocate this rank's symmetric block on the CURRENT device: staging buffers of cap_r / cap_s tuples and room for a filter
+ * of max_filter_bytes; writes the handle peers need (HWBRJ_DIST_HANDLE_BYTES) to handle_out. world: power of two <= 16.
+ * cap_r (cap_s) bounds both a rank's input chunk of R (of S) and the tuples of R (the filter survivors) one rank may own;
+ * a join that exceeds them fails with -2 on every rank (nothing is overrun). The same values on every rank. */
 hwbrj_dist_t * hwbrj_dist_create(int rank, int world, uint64_t cap_r, uint64_t cap_s, uint64_t max_filter_bytes,
                                  void * handle_out);
 /* map the peers; all_handles = the world handles in rank order. Returns 0 on success. */

@@ -68,7 +68,7 @@ def test_staged_probe_with_forced_range_passes():
     {"HWBRJ_HASH_PARTITION": "2", "HWBRJ_RADIX_BITS": "9"},
     {"HWBRJ_RADIX_BITS": "6", "HWBRJ_NUM_PASSES": "1"},             # the reference's NUM_RADIX_BITS / NUM_PASSES knobs
     {"HWBRJ_RADIX_BITS": "6", "HWBRJ_NUM_PASSES": "2"},
-    {"HWBRJ_RADIX_BITS": "12", "HWBRJ_NUM_PASSES": "1"},            # more than 7 bits always take two passes
+    {"HWBRJ_RADIX_BITS": "12", "HWBRJ_NUM_PASSES": "1"},            # one pass caps the fan-out at 2^7: multi-round tables
     {"HWBRJ_HASH_PARTITION": "2", "HWBRJ_RANGE_PASSES": "2", "HWBRJ_PROBE_CTAS": "2"},
 ], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_pipeline_knobs_match_oracle(env):

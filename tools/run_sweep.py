@@ -40,6 +40,13 @@ GRIDS = {
     "test_parameters": dict(sizes=[(128_000_000, 1_024_000_000)], q=[0.001, 0.01, 0.1], filters=["basic", "blocked"],
                             k=[1, 2, 3, 4, 5, 6], B=[256, 512, 1024]),
     "smoke": dict(sizes=[(250_000, 2_000_000)], q=[0.01], filters=["no", "basic", "blocked"], k=[1, 3], B=[512]),
+    # measurements/run.py:205-269 never_single_pass(): 1 vs 2 partitioning passes, with and without a filter
+    # (NUM_PASSES is a compile-time constant there; here the HWBRJ_NUM_PASSES knob of the same binary)
+    "never_single_pass": dict(sizes=[(32_000_000, 1_024_000_000)], q=[0.01, 0.1], filters=["no", "basic", "blocked"],
+                              k=[1, 2, 3], B=[512], m=1 << 28, passes=[1, 2]),
+    # measurements/run.py:272-330 best_bloom_filter_type(): filter sizes around the L2 capacity, k = 1..4
+    "best_bloom_filter_type": dict(sizes=[(128_000_000, 1_024_000_000)], q=[0.01], filters=["basic", "blocked"],
+                                   k=[1, 2, 3, 4], B=[256, 512], m_list=[1 << 28, 1 << 30, 1 << 31]),
 }
 
 
@@ -49,29 +56,39 @@ def main():
     ap.add_argument("--out", default="gpurun_out/sweep.csv")
     ap.add_argument("--algo", default="PRO")
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--gpus", type=int, default=1)
     args = ap.parse_args()
     from hwbloomradixjoin_b200 import build
     build.build_library()
     exe = build.build_driver()
     g = GRIDS[args.grid]
     rows = []
-    for (r, s), q, filt in itertools.product(g["sizes"], g["q"], g["filters"]):
-        m = 1
-        while m < 8 * r:
-            m <<= 1
-        for k, B in (itertools.product(g["k"], g["B"] if filt == "blocked" else g["B"][:1]) if filt != "no" else [(0, 0)]):
-            for _ in range(args.repeat):
-                cmd = [exe, "-a", args.algo, "-n", "1", "-r", str(r), "-s", str(s), "-q", str(q), "-b", filt]
-                if filt != "no":
-                    cmd += ["-m", str(m), "-k", str(k), "-B", str(B)]
-                p = subprocess.run(cmd, capture_output=True, text=True)
-                if p.returncode != 0:
-                    print("failed:", " ".join(cmd), p.stdout[-300:], file=sys.stderr)
-                    continue
-                row = {"r-size": r, "s-size": s, "s-sel": q, "bloom-filter": filt, "bloom-hashes": k, "bloom-size": m,
-                       "bloom-block-size": B, **parse_result(p.stdout)}
-                rows.append(row)
-                print(row, flush=True)
+    for (r, s), q, filt, passes in itertools.product(g["sizes"], g["q"], g["filters"], g.get("passes", [0])):
+        m_auto = 1
+        while m_auto < 8 * r:
+            m_auto <<= 1
+        m_list = g.get("m_list", [g.get("m", m_auto)]) if filt != "no" else [0]
+        for m in m_list:
+            for k, B in (itertools.product(g["k"], g["B"] if filt == "blocked" else g["B"][:1]) if filt != "no" else [(0, 0)]):
+                for _ in range(args.repeat):
+                    cmd = [exe, "-a", args.algo, "-n", "1", "-r", str(r), "-s", str(s), "-q", str(q), "-b", filt]
+                    if filt != "no":
+                        cmd += ["-m", str(m), "-k", str(k), "-B", str(B)]
+                    if args.gpus > 1:
+                        cmd += ["--gpus", str(args.gpus)]
+                    env = dict(os.environ)
+                    if passes:
+                        env["HWBRJ_NUM_PASSES"] = str(passes)
+                    p = subprocess.run(cmd, capture_output=True, text=True, env=env)
+                    if p.returncode != 0:
+                        print("failed:", " ".join(cmd), p.stdout[-300:], file=sys.stderr)
+                        continue
+                    bits = re.search(r"radix bits = (\d+)", p.stdout)
+                    row = {"r-size": r, "s-size": s, "s-sel": q, "bloom-filter": filt, "bloom-hashes": k, "bloom-size": m,
+                           "bloom-block-size": B, "num-passes": passes or "auto", "gpus": args.gpus,
+                           "radix-bits": int(bits.group(1)) if bits else None, **parse_result(p.stdout)}
+                    rows.append(row)
+                    print(row, flush=True)
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
     with open(args.out, "w", newline="") as f:
         w = csv.DictWriter(f, fieldnames=list(rows[0].keys()))
