@@ -65,10 +65,10 @@ struct Control {
     unsigned long long survivors;  // K2 output cursor == filtered (this rank's S chunk)
     unsigned long long n_own_r, n_own_s;  // tuples this rank owns after the level-1 routing
     JoinAccum acc;
-    uint32_t item_counter;
-    uint32_t abort;  // a receive buffer would overflow: the scatter kernels write nothing
+    uint32_t item_counter[4];  // one per group of partitions (see `parts` in run_join)
+    uint32_t abort;  // a buffer would overflow: the scatter kernels do nothing
     uint32_t err;    // barrier time-out
-    uint32_t pad;
+    uint32_t pad[2];
     unsigned long long pair_cursor;  // materialised output pairs
     unsigned long long row[8];       // this rank's result words {matches, cpair, crpay, cspay, ckey, survivors, flags, 0}
     unsigned long long out[8];       // summed over the ranks
@@ -102,6 +102,9 @@ struct Ctx {
     // host-buffer calls: upload S in chunks on a copy stream and probe each chunk as soon as it has landed
     bool overlap_h2d = false;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // several GPUs: every other group of owned bins runs here (see run_join)
+    cudaEvent_t ev_ov[4];
+    int dist_parts = 4;                  // groups of owned level-1 bins per relation (HWBRJ_DIST_PARTS; 1 = no overlap)
     cudaEvent_t ev_copy[2];
     cudaEvent_t ev_chunk[66];
     int hash_partition = 1;  // 0 never, 1 automatic, 2 whenever the slices fit (see pick_mode)
@@ -172,6 +175,9 @@ static void init_ctx() {
     g.stream = g.own_stream;
     for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
+    for (auto& ev : g.ev_ov) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char* s = getenv("HWBRJ_DIST_PARTS")) g.dist_parts = std::max(1, std::min(4, atoi(s)));
     for (auto& ev : g.ev_copy) CK(cudaEventCreate(&ev));
     for (auto& ev : g.ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CrcTables T;
@@ -386,16 +392,17 @@ static void launch_hist(int pmode, const uint2* in, uint64_t n, const unsigned l
 
 template <int LEVEL>
 static void launch_scatter_l(int pmode, const uint2* in, const PeerBufs& stages, uint2* out, const unsigned long long* n_ptr,
-                             uint64_t n, uint32_t* cursor, const PartFn& pf, uint32_t nbins, uint32_t nseg, uint32_t G,
-                             const uint32_t* abort_flag) {
-    const int grid = g.sms * g.occ_scatter;
+                             uint64_t n, uint32_t* cursor, const PartFn& pf, uint32_t nbins, uint32_t seg_lo, uint32_t seg_hi,
+                             uint32_t G, const uint32_t* abort_flag) {
+    // several GPUs: the level-2 pull is NVLink-bound; two CTAs per SM leave room for the kernels it overlaps with
+    const int grid = g.sms * ((LEVEL == 2 && G > 1) ? std::min(g.occ_scatter, 2) : g.occ_scatter);
     const uint32_t* tiles = g.tiles.as<uint32_t>();
     const uint32_t* seg_start = g.segs.as<uint32_t>();
     const uint32_t* seg_cnt = seg_start + (1u << kMaxLevelBits);
 #define HWBRJ_SCATTER(PM)                                                                                              \
     k_scatter<LEVEL, PM><<<grid, kScatterThreads, kScatterSmem, g.stream>>>(in, stages, out, n_ptr, n, tiles, seg_start,  \
-                                                                           seg_cnt, cursor, pf, g.d_crc, nbins, nseg, G, \
-                                                                           abort_flag)
+                                                                           seg_cnt, cursor, pf, g.d_crc, nbins, seg_lo,  \
+                                                                           seg_hi, G, abort_flag)
     switch (pmode) {
         case 0: HWBRJ_SCATTER(0); break;
         case 1: HWBRJ_SCATTER(1); break;
@@ -410,14 +417,14 @@ static void launch_barrier(const Fab& f, Control* ctrl) {
                                       2ll * g.clock_khz * 1000ll);
 }
 
-// Histogram rows of all ranks -> offsets; level-1 scatter of this rank's chunk into its staging buffer (local); level-2
-// scatter of the OWNED level-1 bins, which pulls its input segments from the staging buffers of all ranks. Returns the
-// final partitions of this rank. `hist` is this rank's row (already computed), `rows` where every rank's row is gathered
-// (world > 1), `stages` the staging buffers, `t2` the local level-2 output, `capacity` bounds a chunk and an owner's share.
-static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, const uint2* in, uint64_t n,
-                                  const unsigned long long* n_ptr, uint32_t* hist, const PeerPtrs& rows,
-                                  const PeerBufs& stages, uint64_t capacity, uint32_t* off, uint2* t2,
-                                  unsigned long long* n_own, Control* ctrl, int& launches) {
+// Histogram rows of all ranks -> offsets; level-1 scatter of this rank's chunk into its staging buffer (purely local).
+// Afterwards the level-2 pass (launch_level2) pulls the segments of the OWNED level-1 bins from the staging buffers of all
+// ranks. `hist` is this rank's row (already computed), `rows` where every rank's row is gathered (world > 1), `stages` the
+// staging buffers, `capacity` bounds a chunk and an owner's share. Returns true when a level-2 pass has to follow (always
+// with several GPUs: with b2 == 0 it degenerates to gathering the owned bins from the peers).
+static bool partition_front(const Fab& f, int pmode, const PartFn& pf, const uint2* in, uint64_t n,
+                            const unsigned long long* n_ptr, uint32_t* hist, const PeerPtrs& rows, const PeerBufs& stages,
+                            uint64_t capacity, uint32_t* off, unsigned long long* n_own, Control* ctrl, int& launches) {
     const uint32_t P = 1u << pf.bits;
     const uint32_t b1 = pf.bits - pf.b2;
     const bool dist = f.world > 1;
@@ -436,8 +443,7 @@ static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, con
                                           seg_start + (1u << kMaxLevelBits), n_own, &ctrl->abort);
     TR("K3 scan");
     launches++;
-    uint2* t1 = stages.buf[f.rank];
-    launch_scatter_l<1>(pmode, in, stages, t1, n_ptr, n, g.cur1.as<uint32_t>(), pf, 1u << b1, 0u, 1u,
+    launch_scatter_l<1>(pmode, in, stages, stages.buf[f.rank], n_ptr, n, g.cur1.as<uint32_t>(), pf, 1u << b1, 0u, 0u, 1u,
                         dist ? &ctrl->abort : nullptr);
     TR("K4 scatter level 1");
     launches++;
@@ -445,15 +451,18 @@ static const uint2* run_partition(const Fab& f, int pmode, const PartFn& pf, con
         launch_barrier(f, ctrl);  // every rank's staging buffer is complete
         TR("barrier");
         launches++;
-    } else if (pf.b2 == 0) {
-        return t1;  // one GPU, one pass: the level-1 output is final
     }
-    // several GPUs: always (with b2 == 0 it degenerates to gathering the owned bins from the peers)
-    launch_scatter_l<2>(pmode, nullptr, stages, t2, nullptr, capacity, g.cur2.as<uint32_t>(), pf, 1u << pf.b2, 1u << b1,
-                        (uint32_t)f.world, dist ? &ctrl->abort : nullptr);
-    TR(dist ? "K4 scatter level 2 (pull)" : "K4 scatter level 2");
+    return dist || pf.b2 != 0;
+}
+
+// level-2 pass over the owned level-1 bins [lb0, lb1) into t2
+static void launch_level2(const Fab& f, int pmode, const PartFn& pf, const PeerBufs& stages, uint2* t2, uint32_t lb0,
+                          uint32_t lb1, Control* ctrl, int& launches) {
+    const uint32_t G = (uint32_t)f.world;
+    launch_scatter_l<2>(pmode, nullptr, stages, t2, nullptr, 0, g.cur2.as<uint32_t>(), pf, 1u << pf.b2, lb0 * G, lb1 * G, G,
+                        G > 1 ? &ctrl->abort : nullptr);
+    TR(G > 1 ? "K4 scatter level 2 (pull)" : "K4 scatter level 2");
     launches++;
-    return t2;
 }
 
 static void ensure_workspace(uint64_t capR, uint64_t nS, uint64_t capS, const bloom_filter_args_t* args, bool dist) {
@@ -467,8 +476,8 @@ static void ensure_workspace(uint64_t capR, uint64_t nS, uint64_t capS, const bl
     g.cur2.ensure(P * 4);
     g.tiles.ensure((((size_t)1 << kMaxLevelBits) + 1) * 4);
     g.segs.ensure(((size_t)2 << kMaxLevelBits) * 4);
-    g.work.ensure((P + 1) * 4);
-    g.work_part.ensure((P + capS / kSChunk + 2) * 4);  // one entry per join work item
+    g.work.ensure(4 * (P + 1) * 4);                        // up to 4 groups of partitions, each with its own work list
+    g.work_part.ensure(4 * (P + capS / kSChunk + 2) * 4);  // one entry per join work item
     g.ctrl.ensure(sizeof(Control));
     if (!dist) g.rt1.ensure(std::max<uint64_t>(capR, 1) * 8 + 64);
     g.rp.ensure(std::max<uint64_t>(capR, 1) * 8 + 64);
@@ -607,30 +616,69 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         launches++;
     }
     rec(2);
-    const uint2* Rp = run_partition(f, pmode, pf, dR, nR, nullptr, g.histR.as<uint32_t>(), f.histR, stageR,
-                                    dist ? f.cap_r : nR, g.offR.as<uint32_t>(), g.rp.as<uint2>(), &ctrl->n_own_r, ctrl,
-                                    launches);
-    rec(3);
-    if (args) {
-        bp.filter = my_filter;
-        if (pmode != 0) {  // K1': the filter, slice by slice, from the partitioned R; every word is written
-            const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
-            const uint32_t nbuf = 2u * slice_words * 4u <= 96u * 1024u ? 2u : 1u;
-            const int smem = (int)(nbuf * slice_words * 4u);
-            const int grid = g.sms * (smem <= 48 * 1024 ? 4 : 1);
-            const uint32_t gbase = (uint32_t)f.rank * PL;
-#define HWBRJ_K1P(BL, PE)                                                                                           \
-    k_filter_from_parts<BL, PE><<<grid, 512, smem, g.stream>>>(Rp, g.offR.as<uint32_t>(), PL, gbase, slice_words, bp, \
-                                                               g.d_crc, filt, (uint32_t)f.world, nbuf)
-            if (pmode == 2) {
-                if (dist) HWBRJ_K1P(true, true); else HWBRJ_K1P(true, false);
-            } else {
-                if (dist) HWBRJ_K1P(false, true); else HWBRJ_K1P(false, false);
-            }
+    // Several GPUs: the owned level-1 bins are handled in `parts` groups on two streams, so that the NVLink pull of
+    // group h+1 (inbound traffic) runs while group h is consumed -- on the R side by the filter-slice build, whose stores
+    // into the peers' filters are outbound traffic; on the S side by the join. One GPU: one group, one stream.
+    const uint32_t P1L = (1u << (bits - b2)) / (uint32_t)f.world;
+    uint32_t parts = 1;
+    if (dist && g.dist_parts > 1) parts = std::min<uint32_t>((uint32_t)g.dist_parts, P1L);
+    cudaStream_t main_stream = g.stream;
+    auto stream_of = [&](uint32_t h) { return (parts > 1 && (h & 1u)) ? g.side_stream : main_stream; };
+    auto part_begin = [&](uint32_t h) {  // group h starts on its stream after the pull of group h-1 has finished
+        if (parts == 1) return;
+        if (h == 0) {
+            CK(cudaEventRecord(g.ev_ov[0], main_stream));  // fork: the side stream joins the work of this join
+            CK(cudaStreamWaitEvent(g.side_stream, g.ev_ov[0], 0));
+        } else {
+            CK(cudaStreamWaitEvent(stream_of(h), g.ev_ov[1 + ((h - 1) & 1u)], 0));
+        }
+        g.stream = stream_of(h);
+    };
+    auto part_pulled = [&](uint32_t h) {
+        if (parts > 1) CK(cudaEventRecord(g.ev_ov[1 + (h & 1u)], g.stream));
+    };
+    auto parts_end = [&]() {  // join: everything of both streams is ordered before what follows on the main stream
+        if (parts == 1) return;
+        CK(cudaEventRecord(g.ev_ov[3], g.side_stream));
+        CK(cudaStreamWaitEvent(main_stream, g.ev_ov[3], 0));
+        g.stream = main_stream;
+    };
+    auto launch_k1p = [&](const uint2* Rp, uint32_t p0, uint32_t np) {  // K1' over the local partitions [p0, p0 + np)
+        const uint32_t slice_words = (uint32_t)((args->m >> bits) / 32);
+        const uint32_t nbuf = 2u * slice_words * 4u <= 96u * 1024u ? 2u : 1u;
+        const int smem = (int)(nbuf * slice_words * 4u);
+        const int grid = g.sms * (smem <= 48 * 1024 ? 4 : 1);
+        const uint32_t gbase = (uint32_t)f.rank * PL + p0;
+        const uint32_t* roff = g.offR.as<uint32_t>() + p0;
+#define HWBRJ_K1P(BL, PE)                                                                                              \
+    k_filter_from_parts<BL, PE><<<grid, 512, smem, g.stream>>>(Rp, roff, np, gbase, slice_words, bp, g.d_crc, filt,      \
+                                                               (uint32_t)f.world, nbuf)
+        if (pmode == 2) {
+            if (dist) HWBRJ_K1P(true, true); else HWBRJ_K1P(true, false);
+        } else {
+            if (dist) HWBRJ_K1P(false, true); else HWBRJ_K1P(false, false);
+        }
 #undef HWBRJ_K1P
-            TR("K1' filter slices");
-            launches++;
-        } else if (dist) {  // partial filters are complete on every rank (the barrier after the level-1 scatter)
+        TR("K1' filter slices");
+        launches++;
+    };
+    const uint2* Rp = stageR.buf[f.rank];
+    const bool r_level2 = partition_front(f, pmode, pf, dR, nR, nullptr, g.histR.as<uint32_t>(), f.histR, stageR,
+                                          dist ? f.cap_r : nR, g.offR.as<uint32_t>(), &ctrl->n_own_r, ctrl, launches);
+    if (r_level2) Rp = g.rp.as<uint2>();
+    rec(3);
+    if (args) bp.filter = my_filter;
+    const bool slice_build = args && pmode != 0;  // K1': the filter, slice by slice, from the partitioned R
+    for (uint32_t h = 0; h < parts; h++) {
+        const uint32_t lb0 = h * P1L / parts, lb1 = (h + 1) * P1L / parts;
+        part_begin(h);
+        if (r_level2) launch_level2(f, pmode, pf, stageR, g.rp.as<uint2>(), lb0, lb1, ctrl, launches);
+        part_pulled(h);
+        if (slice_build) launch_k1p(Rp, lb0 << b2, (lb1 - lb0) << b2);
+    }
+    parts_end();
+    if (args) {
+        if (pmode == 0 && dist) {  // partial filters are complete on every rank (the barrier after the level-1 scatter)
             const uint64_t n16 = std::max<uint64_t>(args->m / 8, 16) / 16;
             const uint64_t per = n16 / (uint64_t)f.world;
             k_filter_or_bcast<<<g.sms * 4, 256, 0, g.stream>>>(f.partial, f.filter, (uint32_t)f.world, per * f.rank,
@@ -667,26 +715,39 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     TR("histogram S side");
     launches++;
     // one GPU with a filter: sc -> st1 -> sc ; without: dS -> st1 -> sc ; several GPUs: sc -> own staging -> (pull) -> s2
-    const uint2* Sp = run_partition(f, pmode, pf, Sin, nS, n_dev, g.histS.as<uint32_t>(), f.histS, stageS, dist ? f.cap_s : nS,
-                                    g.offS.as<uint32_t>(), dist ? g.s2.as<uint2>() : g.sc.as<uint2>(), &ctrl->n_own_s, ctrl,
-                                    launches);
+    const uint2* Sp = stageS.buf[f.rank];
+    const bool s_level2 = partition_front(f, pmode, pf, Sin, nS, n_dev, g.histS.as<uint32_t>(), f.histS, stageS,
+                                          dist ? f.cap_s : nS, g.offS.as<uint32_t>(), &ctrl->n_own_s, ctrl, launches);
+    uint2* s_out = dist ? g.s2.as<uint2>() : g.sc.as<uint2>();
+    if (s_level2) Sp = s_out;
     rec(6);
-    k_worklist<<<1, 1024, 0, g.stream>>>(g.offR.as<uint32_t>(), g.offS.as<uint32_t>(), PL, g.work.as<uint32_t>(),
-                                         g.work_part.as<uint32_t>());
-    TR("work list");
-    launches++;
-    if (pmode != 0)
-        k_join<true><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
-            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), PL,
-            (uint32_t)bits, &ctrl->item_counter, &ctrl->acc);
-    else
-        k_join<false><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
-            Rp, g.offR.as<uint32_t>(), Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), PL,
-            (uint32_t)bits, &ctrl->item_counter, &ctrl->acc);
-    TR("K5 join");
-    launches++;
-    g.last_Rp = Rp;
-    g.last_Sp = Sp;
+    const size_t work_stride = (size_t)PL + (dist ? f.cap_s : nS) / kSChunk + 2;
+    for (uint32_t h = 0; h < parts; h++) {
+        const uint32_t lb0 = h * P1L / parts, lb1 = (h + 1) * P1L / parts;
+        const uint32_t p0 = parts == 1 ? 0u : lb0 << b2, np = parts == 1 ? PL : (lb1 - lb0) << b2;
+        part_begin(h);
+        if (s_level2) launch_level2(f, pmode, pf, stageS, s_out, parts == 1 ? 0u : lb0, parts == 1 ? P1L : lb1, ctrl, launches);
+        part_pulled(h);
+        // per-partition build + probe of the group's partitions (its own work list and item counter)
+        uint32_t* work_off = g.work.as<uint32_t>() + (size_t)h * (PL + 1);
+        uint32_t* work_part = g.work_part.as<uint32_t>() + (size_t)h * work_stride;
+        const uint32_t* roff = g.offR.as<uint32_t>() + p0;
+        const uint32_t* soff = g.offS.as<uint32_t>() + p0;
+        k_worklist<<<1, 1024, 0, g.stream>>>(roff, soff, np, work_off, work_part);
+        TR("work list");
+        launches++;
+        if (pmode != 0)
+            k_join<true><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
+                Rp, roff, Sp, soff, work_off, work_part, np, (uint32_t)bits, &ctrl->item_counter[h], &ctrl->acc);
+        else
+            k_join<false><<<g.sms * g.occ_join, kJoinThreads, kJoinSmemBytes, g.stream>>>(
+                Rp, roff, Sp, soff, work_off, work_part, np, (uint32_t)bits, &ctrl->item_counter[h], &ctrl->acc);
+        TR("K5 join");
+        launches++;
+    }
+    parts_end();
+    g.last_Rp = parts > 1 ? nullptr : Rp;
+    g.last_Sp = parts > 1 ? nullptr : Sp;
     g.last_P = PL;
     g.last_bits = (uint32_t)bits;
     g.last_hash = pmode != 0;
@@ -1450,17 +1511,17 @@ static int64_t materialize_last(uint2* d_pairs, uint64_t capacity) {
     if (!g.last_Rp || !g.last_Sp) return -1;
     Control* ctrl = g.ctrl.as<Control>();
     CK(cudaMemsetAsync(&ctrl->acc, 0, sizeof(JoinAccum), g.stream));
-    CK(cudaMemsetAsync(&ctrl->item_counter, 0, sizeof(uint32_t), g.stream));
+    CK(cudaMemsetAsync(&ctrl->item_counter[0], 0, sizeof(uint32_t), g.stream));
     CK(cudaMemsetAsync(&ctrl->pair_cursor, 0, sizeof(unsigned long long), g.stream));
     const int smem = kJoinSmemBytes;
     if (g.last_hash)
         k_join<true, true><<<g.sms * g.occ_join, kJoinThreads, smem, g.stream>>>(
             g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), g.last_P,
-            g.last_bits, &ctrl->item_counter, &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
+            g.last_bits, &ctrl->item_counter[0], &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
     else
         k_join<false, true><<<g.sms * g.occ_join, kJoinThreads, smem, g.stream>>>(
             g.last_Rp, g.offR.as<uint32_t>(), g.last_Sp, g.offS.as<uint32_t>(), g.work.as<uint32_t>(), g.work_part.as<uint32_t>(), g.last_P,
-            g.last_bits, &ctrl->item_counter, &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
+            g.last_bits, &ctrl->item_counter[0], &ctrl->acc, d_pairs, &ctrl->pair_cursor, capacity);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, &ctrl->pair_cursor, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -1520,8 +1581,11 @@ static const uint2* partition_local(int pmode, const PartFn& pf, const uint2* in
     PeerBufs stage;
     memset(&stage, 0, sizeof(stage));
     stage.buf[0] = g.rt1.as<uint2>();
-    return run_partition(f, pmode, pf, in, n, nullptr, g.histR.as<uint32_t>(), f.histR, stage, n, g.offR.as<uint32_t>(),
-                         g.rp.as<uint2>(), &ctrl->n_own_r, ctrl, launches);
+    if (!partition_front(f, pmode, pf, in, n, nullptr, g.histR.as<uint32_t>(), f.histR, stage, n, g.offR.as<uint32_t>(),
+                         &ctrl->n_own_r, ctrl, launches))
+        return stage.buf[0];
+    launch_level2(f, pmode, pf, stage, g.rp.as<uint2>(), 0u, 1u << (pf.bits - pf.b2), ctrl, launches);
+    return g.rp.as<uint2>();
 }
 
 int hwbrj_radix_partition(const tuple_t* in, uint64_t n, int bits, tuple_t* out, uint64_t* offsets) {

@@ -575,35 +575,72 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const uint32_t* __restrict__
     for (int i = 0; i < kBinsPerThread; i++) v[i] = 0u;
     const bool mine = lo < P && lo / PL == rank;
     if (lo < P) {
-        for (uint32_t src = 0; src < G; src++) {
-            const uint32_t* row = hist_all + (size_t)src * P + lo;
-            uint32_t sum = 0;
+        // the rows of two ranks per step, all loads of a step independent (L2 loads: the rows were written by peers)
+        for (uint32_t src = 0; src < G; src += 2u) {
+            const bool two = src + 1u < G;
+            const uint32_t* row0 = hist_all + (size_t)src * P + lo;
+            const uint32_t* row1 = row0 + (two ? P : 0u);
+            uint32_t c0[kBinsPerThread], c1[kBinsPerThread];
+            if (per == (uint32_t)kBinsPerThread) {  // 16 bins per thread: four 128-bit loads per row
 #pragma unroll
-            for (int i = 0; i < kBinsPerThread; i++) {
-                if ((uint32_t)i < per) {
-                    const uint32_t c = row[i];
-                    sum += c;
-                    if (mine) v[i] += c;
+                for (int q = 0; q < kBinsPerThread / 4; q++) {
+                    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(row0) + q);
+                    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(row1) + q);
+                    c0[4 * q] = a.x; c0[4 * q + 1] = a.y; c0[4 * q + 2] = a.z; c0[4 * q + 3] = a.w;
+                    c1[4 * q] = b.x; c1[4 * q + 1] = b.y; c1[4 * q + 2] = b.z; c1[4 * q + 3] = b.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kBinsPerThread; i++) {
+                    c0[i] = (uint32_t)i < per ? __ldcg(row0 + i) : 0u;
+                    c1[i] = (uint32_t)i < per ? __ldcg(row1 + i) : 0u;
                 }
             }
-            if (sum) atomicAdd(&s_bucket[src][lo >> b2], (unsigned long long)sum);
+            uint32_t sum0 = 0, sum1 = 0;
+#pragma unroll
+            for (int i = 0; i < kBinsPerThread; i++) {
+                sum0 += c0[i];
+                sum1 += two ? c1[i] : 0u;
+                if (mine) v[i] += c0[i] + (two ? c1[i] : 0u);
+            }
+            if (sum0) atomicAdd(&s_bucket[src][lo >> b2], (unsigned long long)sum0);
+            if (sum1) atomicAdd(&s_bucket[src + 1u][lo >> b2], (unsigned long long)sum1);
         }
     }
     __syncthreads();
-    if (threadIdx.x < G) {  // one thread per rank: exclusive scan of its row over the <= 128 level-1 bins
-        unsigned long long run = 0;
-        for (uint32_t B = 0; B < P1; B++) {
-            s_lstart[threadIdx.x][B] = run;
-            run += s_bucket[threadIdx.x][B];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (wid < G) {  // warp w: exclusive scan of rank w's row over the <= 128 level-1 bins (4 per lane)
+        unsigned long long c[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t B = lane * 4u + q;
+            c[q] = B < P1 ? s_bucket[wid][B] : 0ull;
+            sum += c[q];
         }
-        if (run > capacity) s_abort = 1u;  // its chunk does not fit its staging buffer
-    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + G) {  // one thread per owner: what it will own
-        const uint32_t o = threadIdx.x - 32u;
+        unsigned long long inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += u;
+        }
+        unsigned long long run = inc - sum;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t B = lane * 4u + q;
+            if (B < P1) s_lstart[wid][B] = run;
+            run += c[q];
+        }
+        if (lane == 31 && inc > capacity) s_abort = 1u;  // its chunk does not fit its staging buffer
+    } else if (wid >= 16 && wid < 16 + G) {  // warp 16+o: what owner o will own
+        const uint32_t o = wid - 16u;
         unsigned long long own = 0;
-        for (uint32_t lb = 0; lb < P1L; lb++)
-            for (uint32_t src = 0; src < G; src++) own += s_bucket[src][o * P1L + lb];
-        if (own > capacity) s_abort = 1u;
-        if (o == rank) *n_own = own;
+        for (uint32_t e = lane; e < P1L * G; e += 32u) own += s_bucket[e % G][o * P1L + e / G];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) own += __shfl_down_sync(0xffffffffu, own, d);
+        if (lane == 0) {
+            if (own > capacity) s_abort = 1u;
+            if (o == rank) *n_own = own;
+        }
     }
     __syncthreads();
     // every rank sees the same rows, so all ranks agree on an overflow
@@ -755,8 +792,8 @@ struct PeerBufs {
 template <int LEVEL>
 __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ tile_off,
                                                     const uint32_t* __restrict__ seg_start,
-                                                    const uint32_t* __restrict__ seg_cnt, uint32_t nseg, uint32_t G,
-                                                    uint32_t b2) {
+                                                    const uint32_t* __restrict__ seg_cnt, uint32_t seg_lo, uint32_t seg_hi,
+                                                    uint32_t G, uint32_t b2) {
     ScatterItem it;
     uint64_t src0;
     if (LEVEL == 1) {
@@ -765,7 +802,7 @@ __device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, c
         it.cbase = 0u;
         it.src = 0u;
     } else {
-        uint32_t lo = 0, hi = nseg;  // segment j with tile_off[j] <= item < tile_off[j+1]
+        uint32_t lo = seg_lo, hi = seg_hi;  // segment j with tile_off[j] <= item < tile_off[j+1]
         while (hi - lo > 1u) {
             uint32_t mid = (lo + hi) >> 1;
             if (tile_off[mid] <= (uint32_t)item) lo = mid; else hi = mid;
@@ -787,7 +824,7 @@ __global__ void __launch_bounds__(kScatterThreads, HWBRJ_SCATTER_MINBLOCKS)
 k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out,
           const unsigned long long* __restrict__ n_ptr, uint64_t n_static, const uint32_t* __restrict__ tile_off,
           const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_cnt, uint32_t* __restrict__ cursor,
-          PartFn pf, const uint32_t* __restrict__ g_crc, uint32_t nbins, uint32_t nseg, uint32_t G,
+          PartFn pf, const uint32_t* __restrict__ g_crc, uint32_t nbins, uint32_t seg_lo, uint32_t seg_hi, uint32_t G,
           const uint32_t* __restrict__ abort_flag) {
     constexpr int PER = kScatterTile / kScatterThreads;
     constexpr int NB = 1 << kMaxLevelBits;
@@ -806,7 +843,10 @@ k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out
     const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;
     const uint32_t b2 = pf.b2;
     const uint32_t submask = (1u << b2) - 1u;
-    const uint64_t nitems = LEVEL == 1 ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[nseg];
+    // LEVEL 2 handles the segments [seg_lo, seg_hi): a launch may cover only a part of the owned bins, so that the pull of
+    // the next part overlaps whatever consumes this one (items are numbered over all segments)
+    const uint64_t item0 = LEVEL == 1 ? 0ull : (uint64_t)tile_off[seg_lo];
+    const uint64_t nitems = LEVEL == 1 ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[seg_hi];
     if (PMODE == 2) load_crc_tab(crc_tab, g_crc);
     if (threadIdx.x == 0) {
         for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
@@ -814,7 +854,7 @@ k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out
     }
     __syncthreads();
     auto issue = [&](uint64_t item, int st) {  // thread 0 only
-        ScatterItem it = scatter_item<LEVEL>(item, n, tile_off, seg_start, seg_cnt, nseg, G, b2);
+        ScatterItem it = scatter_item<LEVEL>(item, n, tile_off, seg_start, seg_cnt, seg_lo, seg_hi, G, b2);
         desc[st] = it;
         const uint2* base = LEVEL == 1 ? in : stages.buf[it.src];  // LEVEL 2: a bulk read over NVLink when src is a peer
         mbar_arrive_expect_tx(&mbar[st], it.bytes);
@@ -822,11 +862,11 @@ k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out
     };
     if (threadIdx.x == 0)
         for (int st = 0; st < kScatterStages; st++) {
-            uint64_t item = (uint64_t)blockIdx.x + (uint64_t)st * gridDim.x;
+            uint64_t item = item0 + (uint64_t)blockIdx.x + (uint64_t)st * gridDim.x;
             if (item < nitems) issue(item, st);
         }
     uint32_t it_local = 0;
-    for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x, it_local++) {
+    for (uint64_t item = item0 + blockIdx.x; item < nitems; item += gridDim.x, it_local++) {
         const int st = it_local % kScatterStages;
         const uint32_t parity = (it_local / kScatterStages) & 1u;
         if (threadIdx.x < NB) hist[threadIdx.x] = 0u;
