@@ -37,6 +37,7 @@ WORKLOADS = {
     "c1_blocked": (128_000_000, 1_024_000_000, 0.01, 1, 1 << 30, 4, 256,
                    "canonical inputs, -b blocked -B 256 -k 4"),
     "c3": (128_000_000, 128_000_000, 1.0, None, 0, 0, 0, "Workload B plain PRO: -r 128000000 -s 128000000"),
+    "c1_quarter": (32_000_000, 256_000_000, 0.01, 0, 1 << 28, 1, 512, "1/4 of the canonical workload (per-GPU sizes of C1 on 8 GPUs when run on 2)"),
     "small": (1_000_000, 8_000_000, 0.01, 0, 1 << 23, 1, 512, "1M x 8M smoke-sized"),
     # q < 0 means: S holds Zipf-distributed foreign keys with exponent -q (mchashjoins -z, create_relation_zipf)
     "c5_zipf": (128_000_000, 1_024_000_000, -1.0, 0, 1 << 30, 1, 512,
@@ -290,8 +291,8 @@ def main():
         dom_ms = phases["ms_probe"]
     else:
         dom_name = "k_build_hist + k_scatter (K3/K4: histogram and radix scatter passes of S)"
-        dom_bytes = 8 * s + 16 * s * (2 if stats[-1]["radix_bits"] > 7 else 1)
-        dom_ms = phases["ms_part_s"]
+        dom_bytes = 8 * s + 16 * s * (2 if stats[-1]["radix_bits"] > 7 else 1)  # histogram read + read/write per scatter pass
+        dom_ms = phases["ms_part_s"]  # histogram + offsets + both scatter passes of S (hwbrj_stats_t.phase_split == 1)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     b_alg = (24 * r + 8 * s + 16 * F + 2 * (m // 8)) if bloom is not None else (24 * r + 24 * s)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",

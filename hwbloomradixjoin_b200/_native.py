@@ -38,7 +38,7 @@ class StatsT(C.Structure):  # hwbrj_stats_t
                 ("ms_probe", C.c_float), ("ms_part_s", C.c_float), ("ms_join", C.c_float), ("ms_h2d", C.c_float),
                 ("ms_e2e", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_int32), ("radix_bits", C.c_int32), ("range_passes", C.c_int32),
-                ("n_gpus", C.c_int32), ("ms_comm", C.c_float), ("reserved", C.c_float * 3),
+                ("n_gpus", C.c_int32), ("ms_comm", C.c_float), ("phase_split", C.c_int32), ("reserved", C.c_float * 2),
                 ("owned_r", C.c_uint64), ("owned_s", C.c_uint64)]
 
     def as_dict(self) -> dict:

@@ -17,6 +17,32 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(local: int) -> str:
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU hangs off: with eight
+    ranks copying from pinned memory at once, buffers that all sit on one socket are limited by that socket's DRAM and
+    by the inter-socket link instead of by the eight PCIe links. Returns a description for the bench line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        cpus = open(f"{base}/local_cpulist").read().strip()
+        node = open(f"{base}/numa_node").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return f"gpu {bdf}: numa {node}, no usable cpu in {cpus}"
+        os.sched_setaffinity(0, ids)
+        return f"gpu {bdf}: numa node {node}, {len(ids)} cpus"
+    except Exception as exc:  # not fatal: the copies are merely slower
+        return f"unbound ({exc})"
+
+
 def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -33,6 +59,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
     os.dup2(2, 1)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if os.environ.get("HWBRJ_NUMA_BIND", "1") == "1" else "off"
     dist.init_process_group("nccl", device_id=device)
     from . import BloomFilterArgs
     from .dist import CudaOps, DistGroup, DistJoinGraph, dist_join
@@ -191,7 +218,7 @@ def main(args, wl, METRIC, UNIT, measured_peak, ClockSampler) -> int:
                 "nvlink": nvlink, "roofline": roofline, "cpu_baseline": None,
                 "e2e": {"value": (r + s) / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (r + s),
                         "d2h_bytes_per_step": 8 * 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                        "api": "hwbrj_dist_join (C ABI) on chunks copied from pinned host memory"},
+                        "api": "hwbrj_dist_join (C ABI) on chunks copied from pinned host memory", "host_numa_binding_rank0": numa},
                 "gpu_launches": int(args.steps * world * launches), "clocks": clocks,
                 "cuda_graph": graph is not None}
         os.write(saved_stdout, (json.dumps(line) + "\n").encode())

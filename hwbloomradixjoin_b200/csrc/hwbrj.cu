@@ -90,7 +90,7 @@ struct Ctx {
     int clock_khz = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev[12];
+    cudaEvent_t ev[14];
     uint32_t* d_crc = nullptr;
     DevBuf filter, histR, histS, offR, offS, cur1, cur2, tiles, segs, work, work_part, ctrl, rt1, rp, sc, st1, s2, inR, inS, scratch;
     // state of the most recent join's partitions (inputs of a materialising k_join pass)
@@ -674,6 +674,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         part_begin(h);
         if (r_level2) launch_level2(f, pmode, pf, stageR, g.rp.as<uint2>(), lb0, lb1, ctrl, launches);
         part_pulled(h);
+        if (parts == 1) rec(11);  // one group: the level-2 pass ends here, the slice build follows
         if (slice_build) launch_k1p(Rp, lb0 << b2, (lb1 - lb0) << b2);
     }
     parts_end();
@@ -728,6 +729,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
         part_begin(h);
         if (s_level2) launch_level2(f, pmode, pf, stageS, s_out, parts == 1 ? 0u : lb0, parts == 1 ? P1L : lb1, ctrl, launches);
         part_pulled(h);
+        if (parts == 1) rec(12);
         // per-partition build + probe of the group's partitions (its own work list and item counter)
         uint32_t* work_off = g.work.as<uint32_t>() + (size_t)h * (PL + 1);
         uint32_t* work_part = g.work_part.as<uint32_t>() + (size_t)h * work_stride;
@@ -767,6 +769,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     rec(8);
     g_tracing = false;
     st.kernel_launches = launches;
+    st.phase_split = parts == 1 ? 1 : 0;
     st.radix_bits = bits;
     st.range_passes = nranges;
     st.n_gpus = f.world;
@@ -799,11 +802,19 @@ static int collect_join(hwbrj_stats_t& st, bool has_filter) {
     st.filtered = has_filter ? (int64_t)h.out[5] : -1;
     st.ms_memset = ms(0, 1);
     st.ms_total = ms(1, 8);
-    st.ms_build = ms(1, 2) + ms(3, 4);  // histogram (+ insert), and the slice build / filter exchange after the scatter
-    st.ms_part_r = ms(2, 3);
-    st.ms_probe = ms(4, 5);
-    st.ms_part_s = ms(5, 6);
-    st.ms_join = ms(6, 8);
+    if (st.phase_split) {  // one group of partitions on one stream: every phase is a contiguous piece of the stream
+        st.ms_build = ms(1, 2) + ms(11, 4);  // histogram of R (+ insert), filter slices from the partitioned R
+        st.ms_part_r = ms(2, 11);            // offsets + level-1 + level-2 scatter of R
+        st.ms_probe = ms(4, 5);
+        st.ms_part_s = ms(5, 12);            // histogram + offsets + level-1 + level-2 scatter of the survivors
+        st.ms_join = ms(12, 8);              // work list + per-partition build/probe + result words
+    } else {  // several GPUs: the level-2 pulls overlap the slice build (R side) and the join (S side) on two streams
+        st.ms_build = ms(1, 2);
+        st.ms_part_r = ms(2, 4);   // routing + level-2 pull + slice build + filter exchange
+        st.ms_probe = ms(4, 5);
+        st.ms_part_s = ms(5, 6);   // histogram + offsets + level-1 scatter + barrier
+        st.ms_join = ms(6, 8);     // level-2 pull + join, pipelined
+    }
     st.owned_r = h.n_own_r;
     st.owned_s = h.n_own_s;
     st.d2h_bytes += sizeof(Control);

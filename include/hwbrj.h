@@ -114,11 +114,11 @@ typedef struct hwbrj_stats_t {
     /* device timings, CUDA events on the library's stream, milliseconds */
     float    ms_total;      /* whole join, inputs resident, filter zeroing excluded (reference timing region) */
     float    ms_memset;     /* zero-fill of the filter and scratch (excluded from ms_total, as :1583 is) */
-    float    ms_build;      /* R: Bloom insert + histogram */
-    float    ms_part_r;     /* R: scatter passes */
+    float    ms_build;      /* R: histogram (+ Bloom insert), filter slices built from the partitioned R */
+    float    ms_part_r;     /* R: offsets + scatter passes */
     float    ms_probe;      /* S: Bloom probe + compaction (the K2 launches) */
     float    ms_part_s;     /* S: histogram + scan + scatter passes */
-    float    ms_join;       /* per-partition build + probe */
+    float    ms_join;       /* work list + per-partition build + probe */
     float    ms_h2d;        /* host->device copies (host-buffer entry points only) */
     float    ms_e2e;        /* wall clock of the whole host-buffer call, incl. copies */
     uint64_t h2d_bytes;
@@ -128,7 +128,9 @@ typedef struct hwbrj_stats_t {
     int32_t  range_passes;    /* filter range passes used by insert/probe */
     int32_t  n_gpus;
     float    ms_comm;         /* reserved */
-    float    reserved[3];
+    int32_t  phase_split;     /* 1: the five phase times are disjoint pieces of one stream (one GPU); 0: several GPUs, the
+                                 level-2 pulls overlap the slice build / the join, see DESIGN.md section 7 */
+    float    reserved[2];
     uint64_t owned_r;         /* R tuples this GPU owns after the routing (host-buffer multi-GPU calls: the maximum) */
     uint64_t owned_s;         /* probe tuples (filter survivors) this GPU owns: the per-GPU load of the join phase */
 } hwbrj_stats_t;
