@@ -114,6 +114,7 @@ struct Ctx {
     int range_passes_override = 0;
     int probe_ctas_per_sm = 0;  // 0 = min(occupancy, 4)
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
+    bool probe_adaptive = true; // K2: L1-allocating probe loads while a warp sees repeated keys (HWBRJ_PROBE_ADAPTIVE)
     bool probe_staged = true;   // k >= 2: probes 2..k run on compacted candidates (k_probe_staged; c1_blocked 12.6 -> 9.4 ms)
     DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
     uint64_t zipf_r = 0;
@@ -192,6 +193,7 @@ static void init_ctx() {
     if (const char* s = getenv("HWBRJ_PROBE_CTAS")) g.probe_ctas_per_sm = std::max(0, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_CARVEOUT")) g.probe_carveout = std::min(100, atoi(s));
     if (const char* s = getenv("HWBRJ_PROBE_STAGED")) g.probe_staged = atoi(s) != 0;
+    if (const char* s = getenv("HWBRJ_PROBE_ADAPTIVE")) g.probe_adaptive = atoi(s) != 0;
     if (const char* s = getenv("HWBRJ_HASH_PARTITION")) g.hash_partition = std::max(0, std::min(2, atoi(s)));
     if (const char* s = getenv("HWBRJ_TRACE")) g.trace = atoi(s) != 0;
     // kernel attributes are per device: every instantiation the pipeline can launch is prepared here
@@ -261,6 +263,7 @@ static BloomParams make_bloom(const bloom_filter_args_t* a, uint32_t seed, uint3
     bp.nranges = 1;
     bp.range_shift = 0;
     bp.range_id = 0;
+    bp.adaptive_ld = g.probe_adaptive ? 1u : 0u;
     return bp;
 }
 

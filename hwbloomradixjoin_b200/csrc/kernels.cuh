@@ -63,6 +63,7 @@ struct BloomParams {
     uint32_t nranges;
     uint32_t range_shift;
     uint32_t range_id;
+    uint32_t adaptive_ld;  // K2: switch to L1-allocating probe loads while a warp sees repeated keys (skewed S)
 };
 
 struct JoinAccum {
@@ -159,13 +160,16 @@ __device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t bas
 #ifndef HWBRJ_PROBE_LD
 #define HWBRJ_PROBE_LD 3
 #endif
-__device__ __forceinline__ uint32_t ld_filter(const BloomParams& bp, const uint32_t* p) {
+// `hot`: warp-uniform hint that the keys of this warp repeat (skewed probe relation, e.g. Zipf): then the L1-allocating
+// load is used for BASIC filters as well, so that the few filter lines every SM keeps asking for are served by its own
+// L1 instead of by one L2 slice (C5, theta = 1: the range pass that holds the hottest key took 7.3 ms, the other 3.3).
+__device__ __forceinline__ uint32_t ld_filter(const BloomParams& bp, const uint32_t* p, bool hot = false) {
 #if HWBRJ_PROBE_LD == 1
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 #elif HWBRJ_PROBE_LD == 2 || HWBRJ_PROBE_LD == 3
-    if (HWBRJ_PROBE_LD == 3 && bp.blocked) return __ldg(p);  // compile-time constant inside K2 (MODE bit 0)
+    if (HWBRJ_PROBE_LD == 3 && (bp.blocked || hot)) return __ldg(p);  // bp.blocked: compile-time constant inside K2
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
@@ -369,6 +373,10 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
         }
         uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
         bool act[2 * kProbeV];
+        // skew detector: do two lanes hold the same key in their first tuple? (never for uniform foreign keys, about
+        // every other batch for Zipf theta = 1)
+        const bool hot = !kBlocked && bp.adaptive_ld &&
+                         __any_sync(0xffffffffu, __popc(__match_any_sync(0xffffffffu, t[0].x)) > 1);
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
             const bool valid = (p0 + (uint64_t)j * 32u) < npairs;
@@ -378,7 +386,7 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
                 bloom_start(bp, crc_tab, e ? t[j].z : t[j].x, base[q], h[q], y[q]);
                 const uint32_t a = base[q] + h[q];
                 act[q] = valid && bloom_in_range(bp, a);
-                w[q] = act[q] ? ld_filter(bp, bp.filter + (a >> 5)) : 0u;  // all first probes in flight together
+                w[q] = act[q] ? ld_filter(bp, bp.filter + (a >> 5), hot) : 0u;  // all first probes in flight together
             }
         }
 #pragma unroll
@@ -789,11 +797,11 @@ struct PeerBufs {
     uint2* buf[kMaxPeers];  // staging buffers of all ranks (peer device pointers mapped into this process)
 };
 
+// tile_off / seg_start / seg_cnt: the CTA's shared-memory copies of the segment tables (LEVEL 2)
 template <int LEVEL>
-__device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* __restrict__ tile_off,
-                                                    const uint32_t* __restrict__ seg_start,
-                                                    const uint32_t* __restrict__ seg_cnt, uint32_t seg_lo, uint32_t seg_hi,
-                                                    uint32_t G, uint32_t b2) {
+__device__ __forceinline__ ScatterItem scatter_item(uint64_t item, uint64_t n, const uint32_t* tile_off,
+                                                    const uint32_t* seg_start, const uint32_t* seg_cnt, uint32_t seg_lo,
+                                                    uint32_t seg_hi, uint32_t G, uint32_t b2) {
     ScatterItem it;
     uint64_t src0;
     if (LEVEL == 1) {
@@ -839,6 +847,8 @@ k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out
     __shared__ ScatterItem desc[kScatterStages];
     __shared__ uint8_t sorted_bin[kScatterTile];
     __shared__ uint32_t crc_tab[PMODE == 2 ? kCrcSmemWords : 1];
+    // LEVEL 2: the segment tables, so that finding a tile's segment is a binary search in shared memory
+    __shared__ uint32_t s_tile_off[LEVEL == 2 ? NB + 1 : 1], s_seg_start[LEVEL == 2 ? NB : 1], s_seg_cnt[LEVEL == 2 ? NB : 1];
     if (abort_flag && *abort_flag) return;  // a buffer would overflow (k_scan_dist): nothing is read or written
     const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;
     const uint32_t b2 = pf.b2;
@@ -848,19 +858,32 @@ k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out
     const uint64_t item0 = LEVEL == 1 ? 0ull : (uint64_t)tile_off[seg_lo];
     const uint64_t nitems = LEVEL == 1 ? (n + kScatterTile - 1) / kScatterTile : (uint64_t)tile_off[seg_hi];
     if (PMODE == 2) load_crc_tab(crc_tab, g_crc);
+    if (LEVEL == 2) {
+        for (uint32_t i = seg_lo + threadIdx.x; i <= seg_hi && i <= (uint32_t)NB; i += kScatterThreads) {
+            s_tile_off[i] = tile_off[i];
+            if (i < seg_hi) {
+                s_seg_start[i] = seg_start[i];
+                s_seg_cnt[i] = seg_cnt[i];
+            }
+        }
+    }
     if (threadIdx.x == 0) {
         for (int st = 0; st < kScatterStages; st++) mbar_init(&mbar[st], 1u);
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](uint64_t item, int st) {  // thread 0 only
-        ScatterItem it = scatter_item<LEVEL>(item, n, tile_off, seg_start, seg_cnt, seg_lo, seg_hi, G, b2);
+    // The bulk loads are issued by a thread that has nothing else to do between the barriers (A) and (C): warp 0 scans
+    // the bin counts and threads 32..159 wait for their cursor atomics there, and all of them would wait for the issue.
+    constexpr uint32_t kIssuer = kScatterThreads - 32;
+    static_assert(kIssuer >= 32u + NB, "the issuing thread must not be a scanning or claiming thread");
+    auto issue = [&](uint64_t item, int st) {  // thread kIssuer only
+        ScatterItem it = scatter_item<LEVEL>(item, n, s_tile_off, s_seg_start, s_seg_cnt, seg_lo, seg_hi, G, b2);
         desc[st] = it;
         const uint2* base = LEVEL == 1 ? in : stages.buf[it.src];  // LEVEL 2: a bulk read over NVLink when src is a peer
         mbar_arrive_expect_tx(&mbar[st], it.bytes);
         bulk_g2s(raw + st * kScatterStageTuples, base + it.src_al, it.bytes, &mbar[st]);
     };
-    if (threadIdx.x == 0)
+    if (threadIdx.x == kIssuer)
         for (int st = 0; st < kScatterStages; st++) {
             uint64_t item = item0 + (uint64_t)blockIdx.x + (uint64_t)st * gridDim.x;
             if (item < nitems) issue(item, st);
@@ -888,7 +911,7 @@ k_scatter(const uint2* __restrict__ in, PeerBufs stages, uint2* __restrict__ out
             }
         }
         __syncthreads();  // (A) every thread holds its tuples in registers: the stage can be refilled
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == kIssuer) {
             uint64_t nxt = item + (uint64_t)kScatterStages * gridDim.x;
             if (nxt < nitems) issue(nxt, st);
         }
