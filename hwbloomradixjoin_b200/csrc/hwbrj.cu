@@ -68,7 +68,8 @@ struct Control {
     uint32_t item_counter[4];  // one per group of partitions (see `parts` in run_join)
     uint32_t abort;  // a buffer would overflow: the scatter kernels do nothing
     uint32_t err;    // barrier time-out
-    uint32_t pad[2];
+    uint32_t skew;   // k_skew_sample: the probe relation repeats keys (selects K2's probe-load flavour)
+    uint32_t pad[1];
     unsigned long long pair_cursor;  // materialised output pairs
     unsigned long long row[8];       // this rank's result words {matches, cpair, crpay, cspay, ckey, survivors, flags, 0}
     unsigned long long out[8];       // summed over the ranks
@@ -104,7 +105,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;  // several GPUs: every other group of owned bins runs here (see run_join)
     cudaEvent_t ev_ov[4];
-    int dist_parts = 4;                  // groups of owned level-1 bins per relation (HWBRJ_DIST_PARTS; 1 = no overlap)
+    int dist_parts = 0;                  // groups of owned level-1 bins per relation (HWBRJ_DIST_PARTS; 0 = by size, 1 = no overlap)
     cudaEvent_t ev_copy[2];
     cudaEvent_t ev_chunk[66];
     int hash_partition = 1;  // 0 never, 1 automatic, 2 whenever the slices fit (see pick_mode)
@@ -114,7 +115,7 @@ struct Ctx {
     int range_passes_override = 0;
     int probe_ctas_per_sm = 0;  // 0 = min(occupancy, 4)
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
-    bool probe_adaptive = true; // K2: L1-allocating probe loads while a warp sees repeated keys (HWBRJ_PROBE_ADAPTIVE)
+    bool probe_adaptive = true; // K2: L1-allocating probe loads when a sample of S shows repeated keys (HWBRJ_PROBE_ADAPTIVE)
     bool probe_staged = true;   // k >= 2: probes 2..k run on compacted candidates (k_probe_staged; c1_blocked 12.6 -> 9.4 ms)
     DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
     uint64_t zipf_r = 0;
@@ -178,7 +179,7 @@ static void init_ctx() {
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
     for (auto& ev : g.ev_ov) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    if (const char* s = getenv("HWBRJ_DIST_PARTS")) g.dist_parts = std::max(1, std::min(4, atoi(s)));
+    if (const char* s = getenv("HWBRJ_DIST_PARTS")) g.dist_parts = std::max(0, std::min(4, atoi(s)));
     for (auto& ev : g.ev_copy) CK(cudaEventCreate(&ev));
     for (auto& ev : g.ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CrcTables T;
@@ -263,7 +264,7 @@ static BloomParams make_bloom(const bloom_filter_args_t* a, uint32_t seed, uint3
     bp.nranges = 1;
     bp.range_shift = 0;
     bp.range_id = 0;
-    bp.adaptive_ld = g.probe_adaptive ? 1u : 0u;
+    bp.skew = nullptr;
     return bp;
 }
 
@@ -624,7 +625,17 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     // into the peers' filters are outbound traffic; on the S side by the join. One GPU: one group, one stream.
     const uint32_t P1L = (1u << (bits - b2)) / (uint32_t)f.world;
     uint32_t parts = 1;
-    if (dist && g.dist_parts > 1) parts = std::min<uint32_t>((uint32_t)g.dist_parts, P1L);
+    if (dist) {
+        // Pipelining pays while a group's kernels are bandwidth-bound. Measured at C1 (profiles/r2_bench_c1_8gpu*.json):
+        // 8 GPUs own 16 M tuples each -- four groups 1.82 ms, two 1.71 ms, one 1.69 ms (a quarter of the slice build is a
+        // latency-bound launch); 2 GPUs own 64 M each and gain from four groups.
+        uint32_t want = (uint32_t)g.dist_parts;
+        if (want == 0) {
+            const uint64_t per_rank = r_total / (uint64_t)f.world;
+            want = per_rank >= (48ull << 20) ? 4u : per_rank >= (24ull << 20) ? 2u : 1u;
+        }
+        parts = std::max(1u, std::min(want, P1L));
+    }
     cudaStream_t main_stream = g.stream;
     auto stream_of = [&](uint32_t h) { return (parts > 1 && (h & 1u)) ? g.side_stream : main_stream; };
     auto part_begin = [&](uint32_t h) {  // group h starts on its stream after the pull of group h-1 has finished
@@ -700,11 +711,22 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     const uint2* Sin = dS;
     const unsigned long long* n_dev = nullptr;
     if (args) {
+        const bool sample = g.probe_adaptive && !bp.blocked && nS > 0;
+        if (sample) bp.skew = &ctrl->skew;
+        if (sample && !feed) {
+            k_skew_sample<<<1, 1024, 0, g.stream>>>(dS, nS, &ctrl->skew);
+            TR("skew sample of S");
+            launches++;
+        }
         if (feed) {  // probe every chunk as soon as its host->device copy has completed
             for (int c = 0; c < feed->nchunks; c++) {
                 const uint64_t off = (uint64_t)c * feed->chunk_tuples;
                 const uint64_t cnt = std::min<uint64_t>(feed->chunk_tuples, nS - off);
                 CK(cudaStreamWaitEvent(g.stream, feed->ev[c], 0));
+                if (sample && c == 0) {  // the first chunk stands for the relation
+                    k_skew_sample<<<1, 1024, 0, g.stream>>>(dS, cnt, &ctrl->skew);
+                    launches++;
+                }
                 launches += run_probe(dS + off, cnt, nullptr, bp, nranges, g.sc.as<uint2>(), &ctrl->survivors);
             }
         } else {

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 #include "hash.cuh"
 
 namespace hwbrj {
@@ -63,7 +64,7 @@ struct BloomParams {
     uint32_t nranges;
     uint32_t range_shift;
     uint32_t range_id;
-    uint32_t adaptive_ld;  // K2: switch to L1-allocating probe loads while a warp sees repeated keys (skewed S)
+    const uint32_t* skew;  // K2: device flag written by k_skew_sample (nullptr = uniform keys assumed)
 };
 
 struct JoinAccum {
@@ -160,9 +161,11 @@ __device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t bas
 #ifndef HWBRJ_PROBE_LD
 #define HWBRJ_PROBE_LD 3
 #endif
-// `hot`: warp-uniform hint that the keys of this warp repeat (skewed probe relation, e.g. Zipf): then the L1-allocating
-// load is used for BASIC filters as well, so that the few filter lines every SM keeps asking for are served by its own
-// L1 instead of by one L2 slice (C5, theta = 1: the range pass that holds the hottest key took 7.3 ms, the other 3.3).
+// `hot`: the probe relation is skewed (k_skew_sample found repeated keys in a sample of S, e.g. Zipf): then the
+// L1-allocating load is used for BASIC filters as well, so that the few filter lines every SM keeps asking for are served by
+// its own L1 instead of by one L2 slice (C5, theta = 1: K2 10.4 -> 6.6 ms). It is a compile-time constant at every call
+// site: K2 holds two copies of its loop and picks one per launch. (Selecting the flavour per load inside one loop cost
+// the uniform case 1.2 ms of 5.5 at C1: profiles/r2_k2_skew_loads.log.)
 __device__ __forceinline__ uint32_t ld_filter(const BloomParams& bp, const uint32_t* p, bool hot = false) {
 #if HWBRJ_PROBE_LD == 1
     uint32_t v;
@@ -276,6 +279,39 @@ __global__ void __launch_bounds__(1024, 2) k_build_hist(const uint2* __restrict_
     }
 }
 
+// ---- skew detector for K2 -------------------------------------------------------------------------------------------
+// One CTA looks at 4096 keys spread evenly over S and counts how many of them it has seen before (open-addressing set in
+// shared memory). Foreign keys drawn from a large domain repeat (almost) never; Zipf-distributed ones, or a small key
+// domain, repeat all the time. *flag = 1 when more than 1/64 of the sample are repeats: K2 then probes with L1-allocating
+// loads (ld_filter). A heuristic that only selects a load flavour -- results never depend on it. 0.013 ms.
+constexpr int kSkewSample = 4096, kSkewSlots = 8192;
+__global__ void __launch_bounds__(1024) k_skew_sample(const uint2* __restrict__ S, uint64_t n, uint32_t* __restrict__ flag) {
+    __shared__ uint32_t slot[kSkewSlots];
+    __shared__ uint32_t repeats;
+    for (int i = threadIdx.x; i < kSkewSlots; i += 1024) slot[i] = 0xFFFFFFFFu;  // (a key equal to the marker counts once less)
+    if (threadIdx.x == 0) repeats = 0u;
+    __syncthreads();
+    const uint64_t nsamp = n < (uint64_t)kSkewSample ? n : (uint64_t)kSkewSample;
+    const uint64_t stride = nsamp ? n / nsamp : 1ull;
+    uint32_t mine = 0u;
+    for (uint64_t i = threadIdx.x; i < nsamp; i += 1024u) {
+        const uint32_t key = S[i * stride].x;
+        uint32_t h = (key * 0x9E3779B1u) >> 19;  // 13 bits
+        for (int probe = 0; probe < kSkewSlots; probe++) {
+            const uint32_t old = atomicCAS(&slot[h], 0xFFFFFFFFu, key);
+            if (old == 0xFFFFFFFFu) break;
+            if (old == key) {
+                mine++;
+                break;
+            }
+            h = (h + 1u) & (kSkewSlots - 1);
+        }
+    }
+    if (mine) atomicAdd(&repeats, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = (nsamp >= 64u && repeats * 64u > (uint32_t)nsamp) ? 1u : 0u;
+}
+
 // ---- K2: Bloom probe + ballot/prefix compaction of survivors ----------------------------------------------------
 // replaces the probe branch of the histogram loop (:794-805), contains_generic (bloom_filter.c:93-111), the
 // contains_cache bitmap (:788,:801,:843) and the `filtered` sum (:1188-1193).
@@ -363,6 +399,8 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
     const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
     constexpr uint64_t kPerIter = 32ull * kProbeV;  // pairs per warp iteration
 
+    auto stream_loop = [&](auto hot_tag) {
+    constexpr bool hot = decltype(hot_tag)::value;
     for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
         const uint64_t p0 = it * kPerIter + lane;
         uint4 t[kProbeV];
@@ -373,10 +411,6 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
         }
         uint32_t base[2 * kProbeV], h[2 * kProbeV], y[2 * kProbeV], w[2 * kProbeV];
         bool act[2 * kProbeV];
-        // skew detector: do two lanes hold the same key in their first tuple? (never for uniform foreign keys, about
-        // every other batch for Zipf theta = 1)
-        const bool hot = !kBlocked && bp.adaptive_ld &&
-                         __any_sync(0xffffffffu, __popc(__match_any_sync(0xffffffffu, t[0].x)) > 1);
 #pragma unroll
         for (int j = 0; j < kProbeV; j++) {
             const bool valid = (p0 + (uint64_t)j * 32u) < npairs;
@@ -398,6 +432,10 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
             surv.drain_if_full(out, out_cursor, pol, lane);
         }
     }
+    };
+    // two copies of the loop, one per probe-load flavour; the choice is uniform over the launch (see ld_filter)
+    if (!kBlocked && bp.skew != nullptr && *bp.skew != 0u) stream_loop(std::true_type{});
+    else stream_loop(std::false_type{});
     if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
     // odd tail tuple
     if ((n & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {

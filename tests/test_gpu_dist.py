@@ -72,12 +72,15 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path):
+@pytest.mark.parametrize("dist_parts", ["0", "4"])
+def test_two_gpu_join_equals_single_gpu(Hgpu, tmp_path, dist_parts):
+    """dist_parts: groups of owned level-1 bins (HWBRJ_DIST_PARTS). "0" = chosen by size (one group at these sizes),
+    "4" = four groups pipelined on two streams, as the large workloads run on 2 GPUs"""
     if Hgpu.device_count() < 2:
         pytest.skip("needs 2 GPUs (one rank per GPU)")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, HWBRJ_ROOT=ROOT, HWBRJ_CASES=json.dumps(CASES))
+    env = dict(os.environ, HWBRJ_ROOT=ROOT, HWBRJ_CASES=json.dumps(CASES), HWBRJ_DIST_PARTS=dist_parts)
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                        capture_output=True, text=True, env=env, timeout=900)

@@ -36,6 +36,10 @@ a_base|
 b_join_u4|-DHWBRJ_JOIN_UNROLL=4
 c_join_u1|-DHWBRJ_JOIN_UNROLL=1
 ' ;;
+r2b) list='
+a_base|
+b_join_book_per_batch|-DHWBRJ_JOIN_PENDING=0
+' ;;
 *) echo "unknown spec $spec"; exit 1 ;;
 esac
 rm -f build/variants/lib_*.so
