@@ -165,7 +165,7 @@ __device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t bas
 // L1-allocating load is used for BASIC filters as well, so that the few filter lines every SM keeps asking for are served by
 // its own L1 instead of by one L2 slice (C5, theta = 1: K2 10.4 -> 6.6 ms). It is a compile-time constant at every call
 // site: K2 holds two copies of its loop and picks one per launch. (Selecting the flavour per load inside one loop cost
-// the uniform case 1.2 ms of 5.5 at C1: profiles/r2_k2_skew_loads.log.)
+// the uniform case 1.2 ms of 5.5 at C1: profiles/r2_kernel_experiments.log.)
 __device__ __forceinline__ uint32_t ld_filter(const BloomParams& bp, const uint32_t* p, bool hot = false) {
 #if HWBRJ_PROBE_LD == 1
     uint32_t v;
