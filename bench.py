@@ -145,6 +145,21 @@ class ClockSampler:
         return out
 
 
+def secondary_bound(s, k, variant, range_passes, k2_ms):
+    """What actually bounds K2 on this part: the L1TEX unit of an SM accepts one wavefront per clock,
+    a divergent probe is one wavefront per key, streaming S costs one wavefront per 128-byte line (16 tuples) and range
+    pass. Only stated for BASIC k <= 1, where a key probes exactly once."""
+    rate = 148 * 1.965  # G wavefronts/s
+    if variant != 0 or k > 1:
+        return {"bound": "l1tex wavefronts", "unit": "G wavefronts/s", "peak": rate, "achieved": None,
+                "note": "not stated for k > 1 / BLOCKED: the number of probes per key depends on the data"}
+    wavefronts = s * max(k, 1) + range_passes * (s // 16)
+    return {"bound": "l1tex wavefronts (1 per SM per clock = 148 x 1.965 GHz): one per probed key + one per 16 streamed "
+                     "tuples and range pass", "unit": "G wavefronts/s", "achieved": wavefronts / (k2_ms * 1e-3) / 1e9,
+            "peak": rate, "frac": wavefronts / (k2_ms * 1e-3) / 1e9 / rate, "wavefronts_per_step": wavefronts,
+            "lower_bound_ms": wavefronts / rate / 1e6, "probes_per_s_G": s * max(k, 1) / (k2_ms * 1e-3) / 1e9}
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,10 +318,7 @@ def main():
                 "note": "achieved = algorithmic bytes of the kernel's launches in one step / their summed CUDA-event time; traffic = ncu DRAM bytes of ONE launch",
                 "launches_per_step": stats[-1]["range_passes"] if bloom is not None else 1,
                 # what actually bounds K2 on this part: one divergent L1TEX access per SM per clock
-                "secondary": None if bloom is None else {
-                    "bound": "l1tex divergent accesses (1 per SM per clock = 148 x 1.965 GHz)", "unit": "G probes/s",
-                    "achieved": s * max(k, 1) / (dom_ms * 1e-3) / 1e9 if variant == 0 and k <= 1 else None,
-                    "peak": 148 * 1.965, "note": "first probes only; every key probes once per join, in the range pass of its bit"},
+                "secondary": None if bloom is None else secondary_bound(s, k, variant, stats[-1]["range_passes"], dom_ms),
                 "whole_join": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak}}
 
