@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(1024) k_skew_sample(const uint2* __restrict__ 
 // together, and appends survivors to its private shared-memory ring; whenever the ring holds kWarpFlush
 // tuples the warp claims kWarpFlush slots of the output with ONE global atomic and writes them as whole
 // 128-byte lines (claims are multiples of kWarpFlush, so every flush but the last is line-aligned).
-constexpr int kProbeWarps = 8;               // warps per CTA
+#ifndef HWBRJ_PROBE_WARPS
+#define HWBRJ_PROBE_WARPS 8
+#endif
+constexpr int kProbeWarps = HWBRJ_PROBE_WARPS;  // warps per CTA (4 and 2 are 10 % slower, 16 the same: r2_kernel_experiments.log)
 
 // per-warp shared-memory ring: tuples are appended with ballot/popc ranks and drained in line-aligned pieces.
 // (Round-2 measurements, profiles/r2_k2_ablation_and_tuning.log: a private output region per warp instead of the shared

@@ -40,6 +40,20 @@ r2b) list='
 a_base|
 b_join_book_per_batch|-DHWBRJ_JOIN_PENDING=0
 ' ;;
+scatter) list='
+a_base|
+b_scatter_t512_m2|-DHWBRJ_SCATTER_THREADS=512 -DHWBRJ_SCATTER_MINBLOCKS=2
+c_scatter_tile4096_t512_m2|-DHWBRJ_SCATTER_TILE=4096 -DHWBRJ_SCATTER_THREADS=512 -DHWBRJ_SCATTER_MINBLOCKS=2
+d_scatter_tile1024_m5|-DHWBRJ_SCATTER_TILE=1024 -DHWBRJ_SCATTER_MINBLOCKS=5
+e_scatter_stages3_m3|-DHWBRJ_SCATTER_STAGES=3 -DHWBRJ_SCATTER_MINBLOCKS=3
+f_scatter_tile4096_t1024_m1|-DHWBRJ_SCATTER_TILE=4096 -DHWBRJ_SCATTER_THREADS=1024 -DHWBRJ_SCATTER_MINBLOCKS=1
+' ;;
+probe_shape) list='
+a_base|
+c_probe_w4_c8|-DHWBRJ_PROBE_WARPS=4
+d_probe_w16_c2|-DHWBRJ_PROBE_WARPS=16
+g_probe_w2_c16|-DHWBRJ_PROBE_WARPS=2
+' ;;
 *) echo "unknown spec $spec"; exit 1 ;;
 esac
 rm -f build/variants/lib_*.so
