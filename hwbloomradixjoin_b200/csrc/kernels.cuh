@@ -35,7 +35,10 @@ constexpr int kTableCap = 8192;                      // R tuples per shared-memo
 #define HWBRJ_SCATTER_MINBLOCKS 4
 #endif
 constexpr int kJoinThreads = HWBRJ_JOIN_THREADS;
-constexpr int kSChunk = 32768;                       // S tuples per join work item
+#ifndef HWBRJ_JOIN_SCHUNK
+#define HWBRJ_JOIN_SCHUNK 32768
+#endif
+constexpr int kSChunk = HWBRJ_JOIN_SCHUNK;            // S tuples per join work item
 constexpr uint32_t kBigItems = 128;                  // partitions with more work items are expanded cooperatively
 constexpr int kScatterThreads = HWBRJ_SCATTER_THREADS;
 constexpr int kScatterTile = HWBRJ_SCATTER_TILE;     // tuples per scatter tile

@@ -54,6 +54,12 @@ c_probe_w4_c8|-DHWBRJ_PROBE_WARPS=4
 d_probe_w16_c2|-DHWBRJ_PROBE_WARPS=16
 g_probe_w2_c16|-DHWBRJ_PROBE_WARPS=2
 ' ;;
+schunk) list='
+a_base|
+b_schunk_64k|-DHWBRJ_JOIN_SCHUNK=65536
+c_schunk_128k|-DHWBRJ_JOIN_SCHUNK=131072
+d_schunk_16k|-DHWBRJ_JOIN_SCHUNK=16384
+' ;;
 *) echo "unknown spec $spec"; exit 1 ;;
 esac
 rm -f build/variants/lib_*.so
