@@ -36,6 +36,7 @@ WORKLOADS = {
            "PR1 ref: -r 16000000 -s 256000000 -q 0.01 -m 134217728 -k 1"),
     "c1_blocked": (128_000_000, 1_024_000_000, 0.01, 1, 1 << 30, 4, 256,
                    "canonical inputs, -b blocked -B 256 -k 4"),
+    "c1_blocked_k1": (128_000_000, 1_024_000_000, 0.01, 1, 1 << 30, 1, 512, "canonical inputs, -b blocked -B 512 -k 1"),
     "c3": (128_000_000, 128_000_000, 1.0, None, 0, 0, 0, "Workload B plain PRO: -r 128000000 -s 128000000"),
     "c1_quarter": (32_000_000, 256_000_000, 0.01, 0, 1 << 28, 1, 512, "1/4 of the canonical workload (per-GPU sizes of C1 on 8 GPUs when run on 2)"),
     "small": (1_000_000, 8_000_000, 0.01, 0, 1 << 23, 1, 512, "1M x 8M smoke-sized"),

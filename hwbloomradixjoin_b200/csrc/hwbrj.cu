@@ -68,7 +68,7 @@ struct Control {
     uint32_t item_counter[4];  // one per group of partitions (see `parts` in run_join)
     uint32_t abort;  // a buffer would overflow: the scatter kernels do nothing
     uint32_t err;    // barrier time-out
-    uint32_t skew;   // k_skew_sample: the probe relation repeats keys (selects K2's probe-load flavour)
+    uint32_t skew;   // k_probe_sample: bit 0 the probe relation repeats keys, bit 1 most of it passes the filter
     uint32_t pad[1];
     unsigned long long pair_cursor;  // materialised output pairs
     unsigned long long row[8];       // this rank's result words {matches, cpair, crpay, cspay, ckey, survivors, flags, 0}
@@ -115,12 +115,12 @@ struct Ctx {
     int range_passes_override = 0;
     int probe_ctas_per_sm = 0;  // 0 = min(occupancy, 4)
     int probe_carveout = -1;    // K2 shared-memory carve-out in percent (-1 = driver default)
-    bool probe_adaptive = true; // K2: L1-allocating probe loads when a sample of S shows repeated keys (HWBRJ_PROBE_ADAPTIVE)
+    bool probe_adaptive = true; // K2's load flavour and shape follow a sample of S (k_probe_sample; HWBRJ_PROBE_ADAPTIVE)
     bool probe_staged = true;   // k >= 2: probes 2..k run on compacted candidates (k_probe_staged; c1_blocked 12.6 -> 9.4 ms)
     DevBuf zipf_lut, zipf_sums;  // cumulated Zipf density of the last (alphabet size, exponent) that was generated
     uint64_t zipf_r = 0;
     double zipf_theta = -1.0;
-    int occ_scatter = 1, occ_join = 1, occ_probe[8] = {0}, occ_staged = 1;
+    int occ_scatter = 1, occ_join = 1, occ_probe[8][2] = {{0}}, occ_staged = 1;
     // HWBRJ_TRACE=1: one CUDA event after every launch of a (non-captured) join; the per-kernel times are printed to stderr
     bool trace = false;
     std::vector<cudaEvent_t> tr_ev;
@@ -147,14 +147,19 @@ static void set_smem(K kernel, int bytes) {
 constexpr int kHistSmem = ((1 << kMaxRadixBits) + kCrcSmemWords) * 4;
 constexpr int kFilterSliceSmemMax = 192 * 1024;
 
+template <int M, int SH>
+static void init_probe_shape() {
+    const int smem = kProbeWarps * ProbeShape<SH>::SMEM_PER_WARP;
+    set_smem(k_probe_compact<M, SH>, smem);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_probe[M][SH], k_probe_compact<M, SH>, kProbeWarps * 32, smem));
+    g.occ_probe[M][SH] = std::max(g.occ_probe[M][SH], 1);
+    if (g.probe_carveout >= 0)
+        CK(cudaFuncSetAttribute(k_probe_compact<M, SH>, cudaFuncAttributePreferredSharedMemoryCarveout, g.probe_carveout));
+}
 template <int M>
 static void init_probe_mode() {
-    const int smem = kProbeWarps * kProbeSmemPerWarp;
-    set_smem(k_probe_compact<M>, smem);
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_probe[M], k_probe_compact<M>, kProbeWarps * 32, smem));
-    g.occ_probe[M] = std::max(g.occ_probe[M], 1);
-    if (g.probe_carveout >= 0)
-        CK(cudaFuncSetAttribute(k_probe_compact<M>, cudaFuncAttributePreferredSharedMemoryCarveout, g.probe_carveout));
+    init_probe_shape<M, 0>();
+    init_probe_shape<M, 1>();
 }
 
 static void init_ctx() {
@@ -208,8 +213,8 @@ static void init_ctx() {
     set_smem(k_join<false, true>, kJoinSmemBytes); set_smem(k_join<true, true>, kJoinSmemBytes);
     init_probe_mode<0>(); init_probe_mode<1>(); init_probe_mode<2>(); init_probe_mode<3>();
     init_probe_mode<4>(); init_probe_mode<5>(); init_probe_mode<6>(); init_probe_mode<7>();
-    set_smem(k_probe_staged<0>, kProbeWarps * kProbeSmemPerWarp); set_smem(k_probe_staged<1>, kProbeWarps * kProbeSmemPerWarp);
-    set_smem(k_probe_staged<4>, kProbeWarps * kProbeSmemPerWarp); set_smem(k_probe_staged<5>, kProbeWarps * kProbeSmemPerWarp);
+    set_smem(k_probe_staged<0>, kProbeWarps * kStagedSmemPerWarp); set_smem(k_probe_staged<1>, kProbeWarps * kStagedSmemPerWarp);
+    set_smem(k_probe_staged<4>, kProbeWarps * kStagedSmemPerWarp); set_smem(k_probe_staged<5>, kProbeWarps * kStagedSmemPerWarp);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_scatter, k_scatter<1, 1>, kScatterThreads, kScatterSmem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_join, k_join<false>, kJoinThreads, kJoinSmemBytes));
     g.occ_scatter = std::max(g.occ_scatter, 1);
@@ -337,32 +342,41 @@ static void trace_print(int rank) {
 
 // ---- kernel dispatch on the compile-time specialisations ---------------------------------------------------------------
 // K2 launch: (blocked, k == 1, ranged)
-static void launch_probe_mode(int mode, const uint2* in, uint64_t n, const unsigned long long* n_ptr, const BloomParams& bp,
-                              uint2* out, unsigned long long* cursor) {
-    const int smem = kProbeWarps * kProbeSmemPerWarp;
+static int launch_probe_mode(int mode, const uint2* in, uint64_t n, const unsigned long long* n_ptr, const BloomParams& bp,
+                             uint2* out, unsigned long long* cursor) {
     if (g.probe_staged && bp.k >= 2u && !(mode & 2)) {  // staged probe for k >= 2 (HWBRJ_PROBE_STAGED=0 switches it off)
+        const int smem = kProbeWarps * kStagedSmemPerWarp;
         const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : 4);
         switch (mode) {
-            case 0: k_probe_staged<0><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
-            case 1: k_probe_staged<1><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
-            case 4: k_probe_staged<4><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
-            case 5: k_probe_staged<5><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return;
+            case 0: k_probe_staged<0><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return 1;
+            case 1: k_probe_staged<1><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return 1;
+            case 4: k_probe_staged<4><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return 1;
+            case 5: k_probe_staged<5><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor); return 1;
             default: break;
         }
     }
-    // measured on B200: 4 CTAs/SM beats the occupancy maximum (more L1 left for the loads in flight)
-#define HWBRJ_PROBE_CASE(M)                                                                                          \
-    case M: {                                                                                                        \
-        const int grid = g.sms * (g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(g.occ_probe[M], 4));          \
-        k_probe_compact<M><<<grid, kProbeWarps * 32, smem, g.stream>>>(in, n, n_ptr, bp, g.d_crc, out, cursor);      \
-        break;                                                                                                       \
+    // measured on B200: ProbeShape::CTAS CTAs/SM beat the occupancy maximum (more L1 left for the loads in flight).
+    // With a sample of S (bp.skew) both shapes are launched and the device-side verdict lets one of them return at once;
+    // without one only the shape for dense survivors runs.
+#define HWBRJ_PROBE_LAUNCH(M, SH)                                                                                      \
+    {                                                                                                                  \
+        const int ctas = g.probe_ctas_per_sm ? g.probe_ctas_per_sm : std::min(g.occ_probe[M][SH], ProbeShape<SH>::CTAS); \
+        k_probe_compact<M, SH><<<g.sms * ctas, kProbeWarps * 32, kProbeWarps * ProbeShape<SH>::SMEM_PER_WARP, g.stream>>>( \
+            in, n, n_ptr, bp, g.d_crc, out, cursor);                                                                   \
     }
+#define HWBRJ_PROBE_CASE(M)                                \
+    case M:                                                \
+        if (bp.skew != nullptr) HWBRJ_PROBE_LAUNCH(M, 0)   \
+        HWBRJ_PROBE_LAUNCH(M, 1)                           \
+        break;
     switch (mode) {
         HWBRJ_PROBE_CASE(0) HWBRJ_PROBE_CASE(1) HWBRJ_PROBE_CASE(2) HWBRJ_PROBE_CASE(3)
         HWBRJ_PROBE_CASE(4) HWBRJ_PROBE_CASE(5) HWBRJ_PROBE_CASE(6) HWBRJ_PROBE_CASE(7)
         default: die("bad probe mode %d", mode);
     }
+#undef HWBRJ_PROBE_LAUNCH
 #undef HWBRJ_PROBE_CASE
+    return bp.skew != nullptr ? 2 : 1;
 }
 
 // all range passes of the S-side probe; returns the number of kernel launches
@@ -371,16 +385,17 @@ static int run_probe(const uint2* dS, uint64_t nS, const unsigned long long* n_p
     const int base_mode = (bp.blocked ? 1 : 0) | (bp.k == 1u ? 2 : 0);
     bp.nranges = (uint32_t)nranges;
     if (nranges == 1) {
-        launch_probe_mode(base_mode, dS, nS, n_ptr, bp, out, cursor);
+        const int l = launch_probe_mode(base_mode, dS, nS, n_ptr, bp, out, cursor);
         TR("K2 probe");
-        return 1;
+        return l;
     }
+    int launches = 0;
     for (int r = 0; r < nranges; r++) {
         bp.range_id = (uint32_t)r;
-        launch_probe_mode(base_mode | 4, dS, nS, n_ptr, bp, out, cursor);
+        launches += launch_probe_mode(base_mode | 4, dS, nS, n_ptr, bp, out, cursor);
         TR("K2 probe (range pass)");
     }
-    return nranges;
+    return launches;
 }
 
 static void launch_hist(int pmode, const uint2* in, uint64_t n, const unsigned long long* n_ptr, const BloomParams& bp,
@@ -711,11 +726,11 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
     const uint2* Sin = dS;
     const unsigned long long* n_dev = nullptr;
     if (args) {
-        const bool sample = g.probe_adaptive && !bp.blocked && nS > 0;
+        const bool sample = g.probe_adaptive && nS > 0;
         if (sample) bp.skew = &ctrl->skew;
         if (sample && !feed) {
-            k_skew_sample<<<1, 1024, 0, g.stream>>>(dS, nS, &ctrl->skew);
-            TR("skew sample of S");
+            k_probe_sample<<<1, 1024, 0, g.stream>>>(dS, nS, bp, g.d_crc, &ctrl->skew);
+            TR("sample of S");
             launches++;
         }
         if (feed) {  // probe every chunk as soon as its host->device copy has completed
@@ -724,7 +739,7 @@ static int run_join(const Fab& f, const uint2* dR, uint64_t nR, const uint2* dS,
                 const uint64_t cnt = std::min<uint64_t>(feed->chunk_tuples, nS - off);
                 CK(cudaStreamWaitEvent(g.stream, feed->ev[c], 0));
                 if (sample && c == 0) {  // the first chunk stands for the relation
-                    k_skew_sample<<<1, 1024, 0, g.stream>>>(dS, cnt, &ctrl->skew);
+                    k_probe_sample<<<1, 1024, 0, g.stream>>>(dS, cnt, bp, g.d_crc, &ctrl->skew);
                     launches++;
                 }
                 launches += run_probe(dS + off, cnt, nullptr, bp, nranges, g.sc.as<uint2>(), &ctrl->survivors);

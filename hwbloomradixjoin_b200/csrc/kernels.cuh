@@ -45,15 +45,31 @@ constexpr int kScatterTile = HWBRJ_SCATTER_TILE;     // tuples per scatter tile
 constexpr int kScatterStages = HWBRJ_SCATTER_STAGES; // TMA bulk-load ring depth
 constexpr int kScatterStageTuples = kScatterTile + 2; // +1 misaligned head, +1 rounding to 16 bytes
 constexpr int kScatterSmem = (kScatterStages * kScatterStageTuples + kScatterTile) * 8;
+// K2 shapes (k_probe_compact<MODE, SHAPE>), measured at C1 / C5 (profiles/r2_kernel_experiments.log):
+//  SHAPE 0, selective filters: 2 x 128-bit loads = 4 keys in flight per lane, 5 CTAs of 8 warps per SM (40 registers),
+//           256-tuple survivor ring per warp (16 KB per CTA: ~150 KB of L1 left for the loads in flight) -- C1 5.17 ms
+//           against 5.53 ms for shape 1; but 12.9 against 6.5 ms when every tuple survives (twice the drains and
+//           cursor atomics);
+//  SHAPE 1, most tuples survive: 8 keys per lane, 4 CTAs per SM, 512-tuple rings.
+// A sample of S probed against the finished filter picks the shape on the device (k_probe_sample): both kernels are
+// launched and the one that was not chosen returns at once.
 #ifndef HWBRJ_PROBE_V
-#define HWBRJ_PROBE_V 4
+#define HWBRJ_PROBE_V 2
 #endif
-#ifdef HWBRJ_PROBE_MINBLOCKS
-#define HWBRJ_PROBE_BOUNDS __launch_bounds__(kProbeWarps * 32, HWBRJ_PROBE_MINBLOCKS)
-#else
-#define HWBRJ_PROBE_BOUNDS __launch_bounds__(kProbeWarps * 32)
+#ifndef HWBRJ_PROBE_MINBLOCKS
+#define HWBRJ_PROBE_MINBLOCKS 5
 #endif
-constexpr int kProbeV = HWBRJ_PROBE_V;               // 128-bit loads in flight per lane in K2
+#ifndef HWBRJ_PROBE_RING
+#define HWBRJ_PROBE_RING 256  // survivor ring per warp (tuples, power of two >= 128)
+#endif
+template <int SHAPE>
+struct ProbeShape {
+    static constexpr int V = SHAPE == 0 ? HWBRJ_PROBE_V : 4;              // 128-bit loads in flight per lane
+    static constexpr int RING = SHAPE == 0 ? HWBRJ_PROBE_RING : 512;      // survivor ring per warp, tuples
+    static constexpr int CTAS = SHAPE == 0 ? HWBRJ_PROBE_MINBLOCKS : 4;   // CTAs per SM
+    static constexpr int SMEM_PER_WARP = RING * 8;
+};
+constexpr int kStagedV = 4;                          // ... and in k_probe_staged (k >= 2), which keeps its measured shape
 
 struct BloomParams {
     uint32_t* filter;      // m/32 words
@@ -67,7 +83,7 @@ struct BloomParams {
     uint32_t nranges;
     uint32_t range_shift;
     uint32_t range_id;
-    const uint32_t* skew;  // K2: device flag written by k_skew_sample (nullptr = uniform keys assumed)
+    const uint32_t* skew;  // K2: verdict of k_probe_sample (nullptr = no sample: uniform keys, dense survivors assumed)
 };
 
 struct JoinAccum {
@@ -164,7 +180,7 @@ __device__ __forceinline__ void bloom_insert(const BloomParams& bp, uint32_t bas
 #ifndef HWBRJ_PROBE_LD
 #define HWBRJ_PROBE_LD 3
 #endif
-// `hot`: the probe relation is skewed (k_skew_sample found repeated keys in a sample of S, e.g. Zipf): then the
+// `hot`: the probe relation is skewed (k_probe_sample found repeated keys in a sample of S, e.g. Zipf): then the
 // L1-allocating load is used for BASIC filters as well, so that the few filter lines every SM keeps asking for are served by
 // its own L1 instead of by one L2 slice (C5, theta = 1: K2 10.4 -> 6.6 ms). It is a compile-time constant at every call
 // site: K2 holds two copies of its loop and picks one per launch. (Selecting the flavour per load inside one loop cost
@@ -282,21 +298,27 @@ __global__ void __launch_bounds__(1024, 2) k_build_hist(const uint2* __restrict_
     }
 }
 
-// ---- skew detector for K2 -------------------------------------------------------------------------------------------
-// One CTA looks at 4096 keys spread evenly over S and counts how many of them it has seen before (open-addressing set in
-// shared memory). Foreign keys drawn from a large domain repeat (almost) never; Zipf-distributed ones, or a small key
-// domain, repeat all the time. *flag = 1 when more than 1/64 of the sample are repeats: K2 then probes with L1-allocating
-// loads (ld_filter). A heuristic that only selects a load flavour -- results never depend on it. 0.013 ms.
+// ---- sample of the probe relation for K2 ---------------------------------------------------------------------------------
+// One CTA looks at 4096 keys spread evenly over S, after the filter is complete, and answers two questions:
+//  bit 0: do keys repeat? (open-addressing set in shared memory; foreign keys drawn from a large domain repeat almost
+//         never, Zipf-distributed ones or a small key domain all the time; set when > 1/64 of the sample are repeats)
+//         -> K2 probes with L1-allocating loads (ld_filter);
+//  bit 1: do most tuples pass the filter? (the sample is probed exactly as K2 probes; set when > 35 % pass)
+//         -> K2 runs in its shape for dense survivors (ProbeShape<1>).
+// A heuristic that only selects a load flavour and a launch shape -- results never depend on it. 0.013 ms.
 constexpr int kSkewSample = 4096, kSkewSlots = 8192;
-__global__ void __launch_bounds__(1024) k_skew_sample(const uint2* __restrict__ S, uint64_t n, uint32_t* __restrict__ flag) {
+__global__ void __launch_bounds__(1024) k_probe_sample(const uint2* __restrict__ S, uint64_t n, BloomParams bp,
+                                                      const uint32_t* __restrict__ g_crc, uint32_t* __restrict__ flag) {
     __shared__ uint32_t slot[kSkewSlots];
-    __shared__ uint32_t repeats;
+    __shared__ uint32_t crc_tab[kCrcSmemWords];
+    __shared__ uint32_t repeats, passes;
     for (int i = threadIdx.x; i < kSkewSlots; i += 1024) slot[i] = 0xFFFFFFFFu;  // (a key equal to the marker counts once less)
-    if (threadIdx.x == 0) repeats = 0u;
+    if (bp.filter != nullptr && bp.blocked) load_crc_tab(crc_tab, g_crc);
+    if (threadIdx.x == 0) repeats = passes = 0u;
     __syncthreads();
     const uint64_t nsamp = n < (uint64_t)kSkewSample ? n : (uint64_t)kSkewSample;
     const uint64_t stride = nsamp ? n / nsamp : 1ull;
-    uint32_t mine = 0u;
+    uint32_t mine = 0u, pass = 0u;
     for (uint64_t i = threadIdx.x; i < nsamp; i += 1024u) {
         const uint32_t key = S[i * stride].x;
         uint32_t h = (key * 0x9E3779B1u) >> 19;  // 13 bits
@@ -309,10 +331,18 @@ __global__ void __launch_bounds__(1024) k_skew_sample(const uint2* __restrict__ 
             }
             h = (h + 1u) & (kSkewSlots - 1);
         }
+        if (bp.filter != nullptr) {  // contains_generic (bloom_filter.c:93-111) on the sampled key
+            uint32_t b0, h0, y0;
+            bloom_start(bp, crc_tab, key, b0, h0, y0);
+            const uint32_t a = b0 + h0;
+            if (bp.k == 0u || bloom_test_rest(bp, b0, h0, y0, __ldg(bp.filter + (a >> 5)))) pass++;
+        }
     }
     if (mine) atomicAdd(&repeats, mine);
+    if (pass) atomicAdd(&passes, pass);
     __syncthreads();
-    if (threadIdx.x == 0) *flag = (nsamp >= 64u && repeats * 64u > (uint32_t)nsamp) ? 1u : 0u;
+    if (threadIdx.x == 0)
+        *flag = ((nsamp >= 64u && repeats * 64u > (uint32_t)nsamp) ? 1u : 0u) | ((passes * 100u > (uint32_t)nsamp * 35u) ? 2u : 0u);
 }
 
 // ---- K2: Bloom probe + ballot/prefix compaction of survivors ----------------------------------------------------
@@ -372,19 +402,22 @@ struct WarpRing {
 // Range passes: pass i probes the keys whose first filter bit lies in range i, so that the probed part of the filter
 // stays L2-resident. (Deferring the keys of later ranges to a buffer instead of re-reading S was measured slower in
 // round 1 -- the deferred writes evict the probed range -- and has been removed.)
-#ifndef HWBRJ_PROBE_RING
-#define HWBRJ_PROBE_RING 512  // survivor ring per warp (tuples, power of two >= 128)
-#endif
-constexpr int kProbeSmemPerWarp = HWBRJ_PROBE_RING * 8;
-template <int MODE>
-__global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, uint64_t n_static,
-                                                   const unsigned long long* __restrict__ n_ptr, BloomParams bp_in,
-                                                   const uint32_t* __restrict__ g_crc, uint2* __restrict__ out,
-                                                   unsigned long long* __restrict__ out_cursor) {
+constexpr int kStagedCandCap = 256, kStagedSurvCap = 256;  // k_probe_staged: candidate ring + survivor ring per warp
+constexpr int kStagedSmemPerWarp = (kStagedCandCap + kStagedSurvCap) * 8;
+template <int MODE, int SHAPE>
+__global__ void __launch_bounds__(kProbeWarps * 32, ProbeShape<SHAPE>::CTAS)
+k_probe_compact(const uint2* __restrict__ S, uint64_t n_static, const unsigned long long* __restrict__ n_ptr,
+                BloomParams bp_in, const uint32_t* __restrict__ g_crc, uint2* __restrict__ out,
+                unsigned long long* __restrict__ out_cursor) {
     constexpr bool kBlocked = (MODE & 1) != 0, kSingle = (MODE & 2) != 0, kRanged = (MODE & 4) != 0;
-    static_assert(HWBRJ_PROBE_RING >= 128, "append2 adds up to 64 tuples between two drain checks");
+    constexpr int kProbeV = ProbeShape<SHAPE>::V, kRing = ProbeShape<SHAPE>::RING;
+    static_assert(kRing >= 128, "append2 adds up to 64 tuples between two drain checks");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
+    // k_probe_sample's verdict: bit 0 = keys repeat (probe-load flavour), bit 1 = most tuples survive (shape 1). Without a
+    // sample (bp.skew == nullptr) only shape 1 is launched.
+    const uint32_t verdict = bp_in.skew != nullptr ? *bp_in.skew : 2u;
+    if (((verdict >> 1) & 1u) != (uint32_t)SHAPE) return;
     BloomParams bp = bp_in;
     bp.blocked = kBlocked ? 1u : 0u;
     if (kSingle) bp.k = 1u;
@@ -396,8 +429,8 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
     const uint64_t n = n_ptr ? min((uint64_t)*n_ptr, n_static) : n_static;  // n_static bounds a device-side count
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    WarpRing<HWBRJ_PROBE_RING> surv;
-    surv.init(reinterpret_cast<uint2*>(smem_raw) + wid * HWBRJ_PROBE_RING);
+    WarpRing<kRing> surv;
+    surv.init(reinterpret_cast<uint2*>(smem_raw) + wid * kRing);
     const uint64_t pol = policy_evict_first();
     const uint64_t npairs = n >> 1;
     const uint4* S4 = reinterpret_cast<const uint4*>(S);
@@ -440,7 +473,7 @@ __global__ void HWBRJ_PROBE_BOUNDS k_probe_compact(const uint2* __restrict__ S, 
     }
     };
     // two copies of the loop, one per probe-load flavour; the choice is uniform over the launch (see ld_filter)
-    if (!kBlocked && bp.skew != nullptr && *bp.skew != 0u) stream_loop(std::true_type{});
+    if (!kBlocked && (verdict & 1u)) stream_loop(std::true_type{});
     else stream_loop(std::false_type{});
     if (surv.count) surv.drain(surv.count, out, out_cursor, pol, lane);
     // odd tail tuple
@@ -470,8 +503,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
                                                                   uint2* __restrict__ out,
                                                                   unsigned long long* __restrict__ out_cursor) {
     constexpr bool kBlocked = (MODE & 1) != 0, kRanged = (MODE & 4) != 0;
-    constexpr int kCandCap = 256, kSurvCap = 256;
-    static_assert((kCandCap + kSurvCap) * 8 == kProbeSmemPerWarp || HWBRJ_PROBE_RING != 512, "smem per warp");
+    constexpr int kCandCap = kStagedCandCap, kSurvCap = kStagedSurvCap;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t crc_tab[kBlocked ? kCrcSmemWords : 1];
     BloomParams bp = bp_in;
@@ -494,7 +526,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
     const uint4* S4 = reinterpret_cast<const uint4*>(S);
     const uint64_t warp_global = (uint64_t)blockIdx.x * kProbeWarps + wid;
     const uint64_t nwarps = (uint64_t)gridDim.x * kProbeWarps;
-    constexpr uint64_t kPerIter = 32ull * kProbeV;
+    constexpr uint64_t kPerIter = 32ull * kStagedV;
 
     // probes 2..k of up to 32 candidates (one per lane); the survivors move to the output ring
     auto finish_batch = [&](uint32_t nb) {
@@ -519,16 +551,16 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
 
     for (uint64_t it = warp_global; it * kPerIter < npairs; it += nwarps) {
         const uint64_t p0 = it * kPerIter + lane;
-        uint4 t[kProbeV];
+        uint4 t[kStagedV];
 #pragma unroll
-        for (int j = 0; j < kProbeV; j++) {
+        for (int j = 0; j < kStagedV; j++) {
             const uint64_t idx = p0 + (uint64_t)j * 32u;
             t[j] = (idx < npairs) ? ld_stream_v4(S4 + idx, pol) : make_uint4(0u, 0u, 0u, 0u);
         }
-        uint32_t a0[2 * kProbeV], w[2 * kProbeV];
-        bool act[2 * kProbeV];
+        uint32_t a0[2 * kStagedV], w[2 * kStagedV];
+        bool act[2 * kStagedV];
 #pragma unroll
-        for (int j = 0; j < kProbeV; j++) {
+        for (int j = 0; j < kStagedV; j++) {
             const bool valid = (p0 + (uint64_t)j * 32u) < npairs;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
@@ -541,7 +573,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) k_probe_staged(const uint2* 
             }
         }
 #pragma unroll
-        for (int j = 0; j < kProbeV; j++) {
+        for (int j = 0; j < kStagedV; j++) {
             const bool fa = act[2 * j] && ((w[2 * j] >> (a0[2 * j] & 31u)) & 1u);
             const bool fb = act[2 * j + 1] && ((w[2 * j + 1] >> (a0[2 * j + 1] & 31u)) & 1u);
             cand.append2(fa, make_uint2(t[j].x, t[j].y), fb, make_uint2(t[j].z, t[j].w), lt);

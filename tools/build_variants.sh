@@ -60,6 +60,37 @@ b_schunk_64k|-DHWBRJ_JOIN_SCHUNK=65536
 c_schunk_128k|-DHWBRJ_JOIN_SCHUNK=131072
 d_schunk_16k|-DHWBRJ_JOIN_SCHUNK=16384
 ' ;;
+k2grid) list='
+a_base|
+b_v2_m6_r256_c6|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=6 -DHWBRJ_PROBE_RING=256
+c_v2_m5_r256_c5|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=256
+d_v2_m4_r512_c4|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=4
+e_v3_m5_r256_c5|-DHWBRJ_PROBE_V=3 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=256
+f_v3_m4_r512_c4|-DHWBRJ_PROBE_V=3 -DHWBRJ_PROBE_MINBLOCKS=4
+g_v3_m4_r256_c4|-DHWBRJ_PROBE_V=3 -DHWBRJ_PROBE_MINBLOCKS=4 -DHWBRJ_PROBE_RING=256
+h_v6_m3_r512_c3|-DHWBRJ_PROBE_V=6 -DHWBRJ_PROBE_MINBLOCKS=3
+i_v5_m3_r512_c3|-DHWBRJ_PROBE_V=5 -DHWBRJ_PROBE_MINBLOCKS=3
+j_v5_m4_r512_c4|-DHWBRJ_PROBE_V=5 -DHWBRJ_PROBE_MINBLOCKS=4
+k_v3_m5_r512_c5|-DHWBRJ_PROBE_V=3 -DHWBRJ_PROBE_MINBLOCKS=5
+' ;;
+k2grid2) list='
+a_base|
+b_v2_m5_r256_c5|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=256
+c_v2_m5_r128_c5|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=128
+d_v2_m6_r128_c6|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=6 -DHWBRJ_PROBE_RING=128
+e_v2_m5_r512_c5|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5
+f_v1_m8_r128_c8|-DHWBRJ_PROBE_V=1 -DHWBRJ_PROBE_MINBLOCKS=8 -DHWBRJ_PROBE_RING=128
+g_v1_m7_r256_c7|-DHWBRJ_PROBE_V=1 -DHWBRJ_PROBE_MINBLOCKS=7 -DHWBRJ_PROBE_RING=256
+h_v2_w16_m3_r256_c3|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_WARPS=16 -DHWBRJ_PROBE_MINBLOCKS=3 -DHWBRJ_PROBE_RING=256
+i_v2_m5_r256_c5_o50|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=256
+j_v2_m5_r256_c5_o25|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=256
+k_v2_m5_r256_c4|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_MINBLOCKS=5 -DHWBRJ_PROBE_RING=256
+l_v2_w4_m10_r256_c10|-DHWBRJ_PROBE_V=2 -DHWBRJ_PROBE_WARPS=4 -DHWBRJ_PROBE_MINBLOCKS=10 -DHWBRJ_PROBE_RING=256
+' ;;
+k2shape) list='
+a_base|
+b_v4_m4_r512|-DHWBRJ_PROBE_V=4 -DHWBRJ_PROBE_MINBLOCKS=4 -DHWBRJ_PROBE_RING=512
+' ;;
 *) echo "unknown spec $spec"; exit 1 ;;
 esac
 rm -f build/variants/lib_*.so
