@@ -312,7 +312,6 @@ static int pick_b2(int bits, int gbits) {
     if (passes <= 0 || bits > kMaxLevelBits) passes = bits > kMaxLevelBits ? 2 : (passes <= 0 ? 1 : passes);
     if (passes == 1 || bits < 2) return 0;
     int b2 = std::min(bits / 2, bits - gbits);  // the owner is a prefix of the level-1 bin
-    if (const char* s = getenv("HWBRJ_L1_BITS")) b2 = bits - std::max(gbits, std::min(atoi(s), bits));  // experiments
     if (bits - b2 > kMaxLevelBits) b2 = bits - kMaxLevelBits;
     if (b2 > kMaxLevelBits) b2 = kMaxLevelBits;  // (then the fan-out shrinks: bits are capped by the caller's override)
     return std::max(b2, 0);
