@@ -184,3 +184,18 @@ def test_bench_line_assembles_with_a_stub_library(monkeypatch, capsys, workload)
         assert key in d["e2e"], key
     assert d["e2e"]["h2d_bytes_per_step"] == 9_216_000_000 and d["e2e"]["d2h_bytes_per_step"] == 136
     assert stub.overlap == 0  # the knob is switched back after the host-buffer leg
+
+
+def test_secondary_bound_of_the_probe():
+    """the wavefront bound of DESIGN.md section 4.4: one L1TEX wavefront per probed key plus one per 16 streamed tuples and
+    range pass, at 148 SMs x 1.965 GHz -- 3.96 ms for C1 (two range passes), stated only where a key probes exactly once"""
+    import bench
+    r, s, q, variant, m, k, B, _ = bench.WORKLOADS["c1"]
+    sec = bench.secondary_bound(s, k, variant, 2, 5.2)
+    assert sec["wavefronts_per_step"] == s + 2 * (s // 16)
+    assert abs(sec["lower_bound_ms"] - 3.961) < 0.01
+    assert abs(sec["frac"] - 3.961 / 5.2) < 0.005
+    one_pass = bench.secondary_bound(256_000_000, 1, 0, 1, 1.03)
+    assert 0.85 < one_pass["frac"] < 0.92                       # C0: 1.03 ms for 256 M keys
+    assert bench.secondary_bound(s, 4, 1, 2, 9.3)["achieved"] is None   # BLOCKED k = 4: probes per key depend on the data
+    assert bench.secondary_bound(s, 3, 0, 1, 9.3)["achieved"] is None   # BASIC k > 1
