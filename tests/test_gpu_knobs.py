@@ -70,7 +70,7 @@ def test_staged_probe_with_forced_range_passes():
     {"HWBRJ_RADIX_BITS": "6", "HWBRJ_NUM_PASSES": "2"},
     {"HWBRJ_RADIX_BITS": "12", "HWBRJ_NUM_PASSES": "1"},            # one pass caps the fan-out at 2^7: multi-round tables
     {"HWBRJ_HASH_PARTITION": "2", "HWBRJ_RANGE_PASSES": "2", "HWBRJ_PROBE_CTAS": "2"},
-    {"HWBRJ_PROBE_ADAPTIVE": "0"},                                  # no skew sample: ld.global.cg probes whatever S looks like
+    {"HWBRJ_PROBE_ADAPTIVE": "0"},                                  # no sample of S: ld.global.cg probes and the dense-survivor shape whatever S looks like
 ], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_pipeline_knobs_match_oracle(env):
     assert _run(env) == []
@@ -111,7 +111,7 @@ print(json.dumps(bad))
 @pytest.mark.parametrize("adaptive", ["1", "0"])
 def test_device_zipf_generator(adaptive):
     """kind 2 of hwbrj_rel_generate: alphabet, cumulated-density table and binary search of genzipf.c on the device; the
-    join of the skewed relation runs K2 with L1-allocating probe loads (k_skew_sample sets the flag) and, with
+    join of the skewed relation runs K2 with L1-allocating probe loads (k_probe_sample sets the bits: repeated keys, dense survivors -> the 8-keys-per-lane shape) and, with
     HWBRJ_PROBE_ADAPTIVE=0, with the loads of the uniform case -- same scalars"""
     p = subprocess.run([sys.executable, "-c", ZIPF_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, HWBRJ_PROBE_ADAPTIVE=adaptive))
